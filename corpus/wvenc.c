@@ -939,10 +939,10 @@ static void encode_pcm_block(encoder *E, stream_state *S, const i32 *srcL, const
             put_meta(o, 0x25, tmp, (cf & 0x2000000) ? 4 : 3);
         }
         if (cfg->extras & WVENC_X_NEW_CONFIG) { tmp[0] = 0; put_meta(o, 0x2a, tmp, 1); }
-        if (cfg->extras & WVENC_X_SAMPLE_RATE) {
-            tmp[0] = (uint8_t)cfg->sample_rate; tmp[1] = (uint8_t)(cfg->sample_rate >> 8); tmp[2] = (uint8_t)(cfg->sample_rate >> 16);
-            put_meta(o, 0x27, tmp, 3);
-        }
+    }
+    if (cfg->extras & WVENC_X_SAMPLE_RATE) { /* every block: blocks are self-describing */
+        tmp[0] = (uint8_t)cfg->sample_rate; tmp[1] = (uint8_t)(cfg->sample_rate >> 8); tmp[2] = (uint8_t)(cfg->sample_rate >> 16);
+        put_meta(o, 0x27, tmp, 3);
     }
     put_meta(o, 0x0a, E->bits, wvlen);
     if (has_wvx || cfg->kind == WVENC_FLOAT) {
