@@ -242,3 +242,65 @@ def format_samples(src, bps, dsd=False):
 
 def md5(b):
     return hashlib.md5(bytes(b)).hexdigest()
+
+
+# ----------------------------------------------------------------------------
+# device-code emulation (tests/emul): the CUDA per-thread decode function compiled for the host.
+# Development/regression aid for boxes without a GPU; never used by the product.
+# ----------------------------------------------------------------------------
+_emul = None
+
+
+def emul():
+    global _emul
+    if _emul is None:
+        from wavpackdecoder_b200 import _native as N
+        src = [os.path.join(ROOT, "tests", "emul", "emul.cpp"), os.path.join(ROOT, "wavpackdecoder_b200", "csrc", "wvb_index.cpp")]
+        deps = src + [os.path.join(ROOT, "wavpackdecoder_b200", "csrc", f) for f in ("wvb_pcm.cuh", "wvb_dsd.cuh", "wvb_plan.h", "wv_tables.h")]
+        deps = [d for d in deps if os.path.exists(d)] + [os.path.join(ROOT, "include", "wvb.h")]
+        path = os.path.join(ROOT, "tests", "emul", "libwvb_emul.so")
+        if not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in deps):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-fwrapv", "-Wno-unknown-pragmas", "-shared", "-pthread",
+                                   "-o", path] + src)
+        lib = C.CDLL(path)
+        N.declare_index_api(lib)
+        lib.emul_decode.argtypes = [C.c_void_p, C.POINTER(N.BlockDesc), C.c_size_t, C.c_void_p, C.c_int, C.POINTER(N.BlockResult)]
+        _emul = lib
+    return _emul
+
+
+def index_file(lib, data, open_flags=0, chunk=4096):
+    """wvb_index over one in-memory file -> (FileInfo, ctypes array of BlockDesc)."""
+    from wavpackdecoder_b200 import _native as N
+    buf = np.frombuffer(data, dtype=np.uint8)
+    info = N.FileInfo()
+    n = C.c_size_t()
+    rc = lib.wvb_index(buf.ctypes.data, buf.size, open_flags, chunk, C.byref(info), None, 0, C.byref(n))
+    assert rc == 0, rc
+    descs = (N.BlockDesc * max(n.value, 1))()
+    info = N.FileInfo()
+    rc = lib.wvb_index(buf.ctypes.data, buf.size, open_flags, chunk, C.byref(info), descs, n.value, C.byref(n))
+    assert rc == 0, rc
+    return info, descs, n.value
+
+
+def emul_decode_file(data, open_flags=0, chunk=4096, out_format=0):
+    """Index + decode one file through the host-compiled device code.
+    Returns (numpy output [int32 or uint8], info, results list)."""
+    from wavpackdecoder_b200 import _native as N
+    lib = emul()
+    info, descs, n = index_file(lib, data, open_flags, chunk)
+    if info.status != 0:
+        raise RuntimeError(info.error_message.decode())
+    nch = info.num_channels if (open_flags & N.OPEN_ALL_CHANNELS) else (info.reduced_channels or info.num_channels)
+    unit = 4 if out_format == 0 else info.bytes_per_sample
+    lib.wvb_rebase(descs, n, 0, 0, out_format, 0)
+    out = np.zeros(info.indexed_samples * nch * unit + 64, dtype=np.uint8)
+    buf = np.frombuffer(data, dtype=np.uint8)
+    padded = np.concatenate([buf, np.zeros(64, dtype=np.uint8)])
+    res = (N.BlockResult * max(n, 1))()
+    lib.emul_decode(padded.ctypes.data, descs, n, out.ctypes.data, out_format, res)
+    out = out[: info.indexed_samples * nch * unit]
+    if out_format == 0:
+        out = out.view(np.int32)
+    return out, info, [res[i] for i in range(n)], [descs[i] for i in range(n)]

@@ -1,0 +1,150 @@
+"""Batch front end over the C ABI: index many in-memory .wv files, decode all their blocks in one
+device pass, hand back per-file PCM / int32 and per-file error counts.
+
+This is plumbing only (buffers, offsets, ctypes); all decode work happens in libwvb.so on the GPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+
+class WvbError(RuntimeError):
+    pass
+
+
+def _check(lib, rc, what):
+    if rc != N.OK:
+        msg = lib.wvb_last_error()
+        raise WvbError("%s failed: %d %s" % (what, rc, msg.decode() if msg else ""))
+
+
+class Corpus:
+    """A set of .wv files packed into one contiguous host slab plus its block table.
+
+    slab: uint8 numpy array (ideally pinned), offsets/sizes: per-file byte ranges.
+    """
+
+    def __init__(self, slab, offsets, sizes, open_flags=0, chunk_samples=4096, out_format=N.OUT_PCM, threads=0):
+        lib = N.load()
+        self.lib = lib
+        self.slab = slab
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self.sizes = np.ascontiguousarray(sizes, dtype=np.uint64)
+        self.nfiles = int(self.offsets.size)
+        self.out_format = out_format
+        self.open_flags = open_flags
+        self.infos = (N.FileInfo * max(self.nfiles, 1))()
+        self.first = np.zeros(self.nfiles, dtype=np.uint64)
+        self.count = np.zeros(self.nfiles, dtype=np.uint64)
+        self.file_out_offset = np.zeros(self.nfiles, dtype=np.uint64)
+        nblocks = C.c_size_t()
+        out_bytes = C.c_uint64()
+        args = (slab.ctypes.data, self.offsets.ctypes.data, self.sizes.ctypes.data, self.nfiles, open_flags, chunk_samples,
+                out_format, threads, self.infos)
+        rc = lib.wvb_index_many(*args, None, 0, self.first.ctypes.data, self.count.ctypes.data, self.file_out_offset.ctypes.data,
+                                C.byref(nblocks), C.byref(out_bytes))
+        _check(lib, rc, "wvb_index_many(count)")
+        self.nblocks = nblocks.value
+        self.descs = (N.BlockDesc * max(self.nblocks, 1))()
+        rc = lib.wvb_index_many(*args, self.descs, self.nblocks, self.first.ctypes.data, self.count.ctypes.data,
+                                self.file_out_offset.ctypes.data, C.byref(nblocks), C.byref(out_bytes))
+        _check(lib, rc, "wvb_index_many")
+        self.out_bytes = int(out_bytes.value)
+
+    @classmethod
+    def from_files(cls, files, **kw):
+        offs, sizes, pos = [], [], 0
+        for f in files:
+            offs.append(pos)
+            sizes.append(len(f))
+            pos += (len(f) + 63) & ~63
+        slab = np.zeros(pos + 64, dtype=np.uint8)
+        for f, o in zip(files, offs):
+            slab[o:o + len(f)] = np.frombuffer(f, dtype=np.uint8)
+        return cls(slab, offs, sizes, **kw)
+
+    @property
+    def total_samples(self):
+        return sum(int(self.infos[i].indexed_samples) for i in range(self.nfiles))
+
+    def file_channels(self, i):
+        info = self.infos[i]
+        if self.open_flags & N.OPEN_ALL_CHANNELS:
+            return info.num_channels
+        return info.reduced_channels or info.num_channels
+
+    def file_output(self, out, i):
+        """Slice of the output slab holding file i (uint8 view for PCM, int32 view for INT32)."""
+        info = self.infos[i]
+        unit = 4 if self.out_format == N.OUT_INT32 else info.bytes_per_sample
+        nbytes = int(info.indexed_samples) * unit * self.file_channels(i)
+        o = int(self.file_out_offset[i])
+        v = out[o:o + nbytes]
+        return v.view(np.int32) if self.out_format == N.OUT_INT32 else v
+
+
+class BatchDecoder:
+    """One wvb_batch (one CUDA device / stream)."""
+
+    def __init__(self, device=0):
+        self.lib = N.load()
+        h = C.c_void_p()
+        _check(self.lib, self.lib.wvb_batch_create(device, C.byref(h)), "wvb_batch_create")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if self.h:
+            self.lib.wvb_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def decode(self, in_ptr, in_bytes, descs, nblocks, out_ptr, out_bytes, out_format, mem_flags=0, results=None):
+        rptr = None
+        if results is not None:
+            rptr = results if isinstance(results, int) else C.addressof(results)
+        rc = self.lib.wvb_batch_decode(self.h, in_ptr, in_bytes, descs, nblocks, out_ptr, out_bytes, out_format, mem_flags, rptr)
+        _check(self.lib, rc, "wvb_batch_decode")
+
+    def prepare(self, descs, nblocks, out_format):
+        _check(self.lib, self.lib.wvb_batch_prepare(self.h, descs, nblocks, out_format), "wvb_batch_prepare")
+
+    def wait(self):
+        _check(self.lib, self.lib.wvb_batch_wait(self.h), "wvb_batch_wait")
+
+    def timing(self):
+        k, h, d, n = C.c_float(), C.c_float(), C.c_float(), C.c_int()
+        _check(self.lib, self.lib.wvb_batch_timing(self.h, C.byref(k), C.byref(h), C.byref(d), C.byref(n)), "wvb_batch_timing")
+        return dict(kernel_ms=k.value, h2d_ms=h.value, d2h_ms=d.value, launches=n.value)
+
+    def decode_corpus(self, corpus, out=None):
+        """Host-buffer decode of a whole Corpus.  Returns (out uint8 array, results array)."""
+        if out is None:
+            out = np.zeros(corpus.out_bytes + 64, dtype=np.uint8)
+        results = (N.BlockResult * max(corpus.nblocks, 1))()
+        self.decode(corpus.slab.ctypes.data, corpus.slab.size, corpus.descs, corpus.nblocks, out.ctypes.data, corpus.out_bytes,
+                    corpus.out_format, 0, results)
+        return out, results
+
+
+def decode_files(files, open_flags=0, chunk_samples=4096, out_format=N.OUT_INT32, device=0):
+    """Convenience: decode a list of .wv byte strings; returns list of (numpy array, crc_errors, info)."""
+    corpus = Corpus.from_files(files, open_flags=open_flags, chunk_samples=chunk_samples, out_format=out_format)
+    dec = BatchDecoder(device)
+    try:
+        out, results = dec.decode_corpus(corpus)
+    finally:
+        dec.close()
+    res = []
+    for i in range(corpus.nfiles):
+        f, c = int(corpus.first[i]), int(corpus.count[i])
+        errs = sum(1 for k in range(f, f + c) if results[k].rflags & N.RF_CRC_ERROR)
+        res.append((corpus.file_output(out, i).copy(), errs, corpus.infos[i], [results[k] for k in range(f, f + c)]))
+    return res

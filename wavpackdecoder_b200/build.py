@@ -1,0 +1,47 @@
+"""Build libwvb.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+    python -m wavpackdecoder_b200.build [--force]
+
+nvcc cross-compiles without a GPU; the .so travels to the GPU box with the repo snapshot.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libwvb.so")
+SOURCES = ["wvb_cuda.cu", "wvb_index.cpp"]
+HEADERS = ["wvb_pcm.cuh", "wvb_dsd.cuh", "wvb_plan.h", "wv_tables.h", os.path.join("..", "..", "include", "wvb.h")]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC,-fwrapv,-O2",
+    "-cudart", "static", "--expt-relaxed-constexpr", "-Xptxas", "-v",
+]
+
+
+def stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    if not force and not stale():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, f) for f in SOURCES]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    log = r.stdout + r.stderr
+    with open(os.path.join(HERE, "build.log"), "w") as f:
+        f.write(" ".join(cmd) + "\n" + log)
+    if r.returncode != 0:
+        sys.stderr.write(log)
+        raise RuntimeError("nvcc failed building libwvb.so")
+    if verbose:
+        print(log)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)

@@ -1,0 +1,346 @@
+// wvb_cuda.cu -- CUDA side of libwvb: kernels, launch planning, the wvb_batch_* C ABI.
+//
+// Execution model: WavPack blocks are independent, each one a strictly serial
+// chain (adaptive Golomb words -> adaptive decorrelation).  One block is decoded by one
+// THREAD; a warp decodes 32 blocks in lock step.  The planner sorts blocks so that a warp
+// holds blocks with the same kernel variant, the same decorrelation term list and the same
+// length, which keeps the warp convergent.  Per-thread decorrelation state lives in shared
+// memory laid out [slot][thread] (bank == lane for any per-lane slot index).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "wvb_dsd.cuh"
+#include "wvb_pcm.cuh"
+#include "wvb_plan.h"
+
+namespace {
+
+constexpr int CTA_THREADS = 128;
+
+thread_local std::string g_last_error;
+int set_error(int code, const std::string &msg)
+{
+    g_last_error = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                     \
+    do {                                                                                                   \
+        cudaError_t e__ = (expr);                                                                          \
+        if (e__ != cudaSuccess) return set_error(WVB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+struct Launch { int variant; int cls; uint32_t first, count; };
+
+struct SharedColumn { // word i of this thread's column; [slot][thread] layout
+    int *base;
+    __device__ __forceinline__ int &operator()(int i) { return base[i * CTA_THREADS]; }
+};
+
+template <bool STEREO, bool HYB, bool GENFIX>
+__global__ void __launch_bounds__(CTA_THREADS)
+k_decode_pcm(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ descs, const uint32_t *__restrict__ order,
+             uint32_t count, uint8_t *__restrict__ out, int out_format, wvb_block_result *__restrict__ results)
+{
+    extern __shared__ int smem[];
+    const uint32_t i = blockIdx.x * CTA_THREADS + threadIdx.x;
+    if (i >= count) return;
+    const uint32_t bi = order[i];
+    SharedColumn SM{smem + threadIdx.x};
+    wvb::decode_block_pcm<STEREO, HYB, GENFIX>(SM, in, descs[bi], out, out_format, &results[bi]);
+}
+
+} // namespace
+
+struct wvb_batch {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // h2d0,h2d1(k0),k1,d2h1
+    uint8_t *d_in = nullptr; size_t d_in_cap = 0;
+    uint8_t *d_out = nullptr; size_t d_out_cap = 0;
+    wvb_block_desc *d_descs = nullptr; size_t d_descs_cap = 0;
+    uint32_t *d_order = nullptr; size_t d_order_cap = 0;
+    wvb_block_result *d_results = nullptr; size_t d_results_cap = 0;
+    std::vector<uint32_t> order;
+    std::vector<Launch> plan;
+    size_t prepared_n = 0; bool prepared = false; int prepared_fmt = -1;
+    std::vector<wvb_block_result> host_results;
+    wvb_block_result *pending_results = nullptr; size_t pending_n = 0; bool pending_copy = false;
+    int launches = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    bool timed = false;
+};
+
+namespace {
+
+template <class T> int ensure(T *&p, size_t &cap, size_t need)
+{
+    if (need <= cap) return WVB_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = need + need / 8 + 256;
+    CUDA_TRY(cudaMalloc((void **)&p, want * sizeof(T)));
+    cap = want;
+    return WVB_OK;
+}
+
+typedef void (*pcm_kernel_t)(const uint8_t *, const wvb_block_desc *, const uint32_t *, uint32_t, uint8_t *, int, wvb_block_result *);
+
+pcm_kernel_t pcm_kernel(int variant)
+{
+    switch (variant) {
+    case wvb::V_MONO: return k_decode_pcm<false, false, false>;
+    case wvb::V_STEREO: return k_decode_pcm<true, false, false>;
+    case wvb::V_MONO | wvb::V_GENFIX: return k_decode_pcm<false, false, true>;
+    case wvb::V_STEREO | wvb::V_GENFIX: return k_decode_pcm<true, false, true>;
+    case wvb::V_MONO | wvb::V_GENFIX | wvb::V_HYBRID: return k_decode_pcm<false, true, true>;
+    case wvb::V_STEREO | wvb::V_GENFIX | wvb::V_HYBRID: return k_decode_pcm<true, true, true>;
+    default: return nullptr;
+    }
+}
+
+// shared-memory size classes (words per thread); a launch uses the smallest class that fits its blocks
+const int kSmemClasses[] = {32, 64, 96, 128, 192, 256, 320, 448};
+int smem_class(int words)
+{
+    for (int c : kSmemClasses)
+        if (words <= c) return c;
+    return -1;
+}
+
+// Sort blocks so that warps are homogeneous; emit one launch per (variant, smem class).
+void make_plan(const wvb_block_desc *descs, size_t n, std::vector<uint32_t> &order, std::vector<Launch> &launches)
+{
+    order.resize(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::vector<uint64_t> key(n);
+    for (size_t i = 0; i < n; i++) {
+        const wvb_block_desc &d = descs[i];
+        int v = wvb::variant_of(d);
+        int cls = v == wvb::V_DSD ? wvb::dsd_mode_class(d) : smem_class(d.smem_words);
+        uint64_t clsbits = (uint64_t)(cls < 0 ? 1023 : cls) & 1023;
+        // variant | class | term signature (16 bits) | inverted length (so long blocks start first)
+        key[i] = ((uint64_t)v << 58) | (clsbits << 48) | ((uint64_t)(d.terms_sig & 0xffff) << 32) | (uint64_t)(0xffffffffu - d.block_samples);
+    }
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key[a] != key[b] ? key[a] < key[b] : a < b; });
+    launches.clear();
+    size_t i = 0;
+    while (i < n) {
+        uint64_t k = key[order[i]] >> 48;
+        size_t j = i;
+        while (j < n && (key[order[j]] >> 48) == k) j++;
+        Launch L;
+        L.variant = (int)(k >> 10);
+        L.cls = (int)(k & 1023);
+        L.first = (uint32_t)i;
+        L.count = (uint32_t)(j - i);
+        launches.push_back(L);
+        i = j;
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+int wvb_abi_version(void) { return WVB_ABI_VERSION; }
+const char *wvb_last_error(void) { return g_last_error.c_str(); }
+
+int wvb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int wvb_batch_create(int device, wvb_batch **out)
+{
+    if (!out) return WVB_E_ARG;
+    *out = nullptr;
+    int n = wvb_device_count();
+    if (n <= 0) return set_error(WVB_E_NO_DEVICE, "no CUDA device: libwvb has no CPU decode path");
+    if (device < 0 || device >= n) return set_error(WVB_E_ARG, "bad device ordinal");
+    CUDA_TRY(cudaSetDevice(device));
+    wvb_batch *b = new wvb_batch();
+    b->device = device;
+    CUDA_TRY(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    for (auto &e : b->ev) CUDA_TRY(cudaEventCreate(&e));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    b->sm_count = prop.multiProcessorCount;
+    b->smem_optin = prop.sharedMemPerBlockOptin;
+    *out = b;
+    return WVB_OK;
+}
+
+void wvb_batch_destroy(wvb_batch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    cudaFree(b->d_in); cudaFree(b->d_out); cudaFree(b->d_descs); cudaFree(b->d_order); cudaFree(b->d_results);
+    for (auto &e : b->ev) if (e) cudaEventDestroy(e);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+void *wvb_batch_stream(wvb_batch *b) { return b ? (void *)b->stream : nullptr; }
+
+int wvb_batch_wait(wvb_batch *b)
+{
+    if (!b) return WVB_E_ARG;
+    CUDA_TRY(cudaSetDevice(b->device));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    if (b->pending_copy && b->pending_results) {
+        memcpy(b->pending_results, b->host_results.data(), b->pending_n * sizeof(wvb_block_result));
+        b->pending_copy = false;
+    }
+    return WVB_OK;
+}
+
+int wvb_batch_timing(wvb_batch *b, float *kernel_ms, float *h2d_ms, float *d2h_ms, int *launches)
+{
+    if (!b || !b->timed) return WVB_E_ARG;
+    CUDA_TRY(cudaSetDevice(b->device));
+    float v = 0;
+    if (h2d_ms) { CUDA_TRY(cudaEventElapsedTime(&v, b->ev[0], b->ev[1])); *h2d_ms = v; }
+    if (kernel_ms) { CUDA_TRY(cudaEventElapsedTime(&v, b->ev[1], b->ev[2])); *kernel_ms = v; }
+    if (d2h_ms) { CUDA_TRY(cudaEventElapsedTime(&v, b->ev[2], b->ev[3])); *d2h_ms = v; }
+    if (launches) *launches = b->launches;
+    return WVB_OK;
+}
+
+static int validate_table(const wvb_block_desc *descs, size_t nblocks, size_t in_bytes, size_t out_bytes, int out_format)
+{
+    for (size_t i = 0; i < nblocks; i++) { // every descriptor must stay inside the slabs (protects the device from bad tables)
+        const wvb_block_desc &d = descs[i];
+        if (d.in_offset + d.in_bytes > in_bytes) return set_error(WVB_E_ARG, "descriptor input range outside the slab");
+        uint64_t fb = wvb_frame_bytes(&d, out_format == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : out_format);
+        uint64_t lo = d.out_offset - (uint64_t)d.gap_before * fb, hi = d.out_offset + (uint64_t)d.block_samples * fb;
+        if (lo > d.out_offset || hi > out_bytes) return set_error(WVB_E_ARG, "descriptor output range outside the slab");
+        for (int k = 0; k < WVB_SUB_COUNT; k++)
+            if (d.sub_off[k] && (uint64_t)d.sub_off[k] + d.sub_len[k] > d.in_bytes) return set_error(WVB_E_ARG, "sub-block outside its block");
+    }
+    return WVB_OK;
+}
+
+static int upload_table(wvb_batch *b, const wvb_block_desc *descs, size_t nblocks)
+{
+    int rc;
+    make_plan(descs, nblocks, b->order, b->plan);
+    if ((rc = ensure(b->d_descs, b->d_descs_cap, nblocks + 1)) != WVB_OK) return rc;
+    if ((rc = ensure(b->d_order, b->d_order_cap, nblocks + 1)) != WVB_OK) return rc;
+    if (nblocks) {
+        CUDA_TRY(cudaMemcpyAsync(b->d_descs, descs, nblocks * sizeof(wvb_block_desc), cudaMemcpyHostToDevice, b->stream));
+        CUDA_TRY(cudaMemcpyAsync(b->d_order, b->order.data(), nblocks * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream));
+    }
+    return WVB_OK;
+}
+
+int wvb_batch_prepare(wvb_batch *b, const wvb_block_desc *descs, size_t nblocks, int out_format)
+{
+    if (!b || !descs) return WVB_E_ARG;
+    if (nblocks > 0xfffffff0ull) return WVB_E_ARG;
+    CUDA_TRY(cudaSetDevice(b->device));
+    b->prepared = false;
+    int rc = validate_table(descs, nblocks, ~(size_t)0 >> 1, ~(size_t)0 >> 1, out_format);
+    if (rc != WVB_OK) return rc;
+    if ((rc = upload_table(b, descs, nblocks)) != WVB_OK) return rc;
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    b->prepared = true;
+    b->prepared_n = nblocks;
+    b->prepared_fmt = out_format;
+    return WVB_OK;
+}
+
+int wvb_batch_decode(wvb_batch *b, const uint8_t *in, size_t in_bytes, const wvb_block_desc *descs, size_t nblocks, void *out,
+                     size_t out_bytes, int out_format, uint32_t mem_flags, wvb_block_result *results)
+{
+    if (!b || !in || !out) return WVB_E_ARG;
+    if (out_format != WVB_OUT_INT32 && out_format != WVB_OUT_PCM && out_format != WVB_OUT_DSD_RAW) return WVB_E_ARG;
+    if (nblocks > 0xfffffff0ull) return WVB_E_ARG;
+    if (!descs && !(b->prepared && b->prepared_n == nblocks && b->prepared_fmt == out_format))
+        return set_error(WVB_E_ARG, "descs == NULL needs a matching wvb_batch_prepare");
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t s = b->stream;
+    b->timed = false;
+    b->launches = 0;
+    int rc;
+    if (descs) {
+        b->prepared = false;
+        if ((rc = validate_table(descs, nblocks, in_bytes, out_bytes, out_format)) != WVB_OK) return rc;
+    }
+
+    CUDA_TRY(cudaEventRecord(b->ev[0], s));
+    const uint8_t *din = in;
+    if (!(mem_flags & WVB_IN_DEVICE)) {
+        if ((rc = ensure(b->d_in, b->d_in_cap, in_bytes + 64)) != WVB_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(b->d_in, in, in_bytes, cudaMemcpyHostToDevice, s));
+        din = b->d_in;
+    }
+    uint8_t *dout = (uint8_t *)out;
+    if (!(mem_flags & WVB_OUT_DEVICE)) {
+        if ((rc = ensure(b->d_out, b->d_out_cap, out_bytes + 64)) != WVB_OK) return rc;
+        dout = b->d_out;
+    }
+    wvb_block_result *dres;
+    if (mem_flags & WVB_RESULTS_DEVICE) {
+        if (!results) return WVB_E_ARG;
+        dres = results;
+    } else {
+        if ((rc = ensure(b->d_results, b->d_results_cap, nblocks + 1)) != WVB_OK) return rc;
+        dres = b->d_results;
+    }
+    if (descs && (rc = upload_table(b, descs, nblocks)) != WVB_OK) return rc;
+    CUDA_TRY(cudaEventRecord(b->ev[1], s));
+
+    const int fmt = out_format;
+    for (const Launch &L : b->plan) {
+        if (L.variant == wvb::V_DSD) {
+            if ((rc = wvb::launch_dsd(L.cls, din, b->d_descs, b->d_order + L.first, L.count, dout, fmt, dres, s, b->smem_optin)) != WVB_OK)
+                return set_error(rc, std::string("DSD launch: ") + cudaGetErrorString(cudaGetLastError()));
+            b->launches++;
+            continue;
+        }
+        pcm_kernel_t k = pcm_kernel(L.variant);
+        if (!k || L.cls <= 0 || L.cls > 448) return set_error(WVB_E_ARG, "block needs more decorrelation state than any kernel class provides");
+        size_t smem = (size_t)L.cls * CTA_THREADS * sizeof(int);
+        if (smem > b->smem_optin) return set_error(WVB_E_ARG, "shared memory class exceeds the device limit");
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        unsigned grid = (L.count + CTA_THREADS - 1) / CTA_THREADS;
+        k<<<grid, CTA_THREADS, smem, s>>>(din, b->d_descs, b->d_order + L.first, L.count, dout, fmt == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : fmt, dres);
+        CUDA_TRY(cudaGetLastError());
+        b->launches++;
+    }
+    CUDA_TRY(cudaEventRecord(b->ev[2], s));
+
+    if (!(mem_flags & WVB_OUT_DEVICE)) CUDA_TRY(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, s));
+    b->pending_copy = false;
+    if (results && !(mem_flags & WVB_RESULTS_DEVICE)) {
+        b->host_results.resize(nblocks);
+        if (nblocks) CUDA_TRY(cudaMemcpyAsync(b->host_results.data(), dres, nblocks * sizeof(wvb_block_result), cudaMemcpyDeviceToHost, s));
+        b->pending_results = results;
+        b->pending_n = nblocks;
+        b->pending_copy = true;
+    }
+    CUDA_TRY(cudaEventRecord(b->ev[3], s));
+    b->timed = true;
+    if (!(mem_flags & WVB_NO_SYNC)) return wvb_batch_wait(b);
+    return WVB_OK;
+}
+
+void *wvb_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void wvb_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+} // extern "C"

@@ -1,0 +1,788 @@
+// wvb_pcm.cuh -- per-thread WavPack PCM block decoder (one block per thread, 32 blocks per warp in lock step).
+//
+// Device restatement of the reference's PCM hot path:
+//   metadata contents   UnpackUtils.cs:156-382, WordsUtils.cs:75-187, FloatUtils.cs:15-30
+//   bit reader          BitsUtils.cs:15-146           -> 64-bit window refilled 32 bits at a time
+//   get_words           WordsUtils.cs:272-511         -> decode_word<>
+//   decorr_*_pass*      UnpackUtils.cs:688-1240       -> per-sample streaming form, state in
+//                                                        shared memory laid out [slot][thread] (bank == lane, conflict free)
+//   unpack_samples      UnpackUtils.cs:510-686        -> joint stereo, mute check, CRC, FALSE_STEREO
+//   fixup_samples       UnpackUtils.cs:1251-1404, FloatUtils.cs:32-56
+//   WavpackFormatSamples WavPackUtils.cs:288-341      -> fused into the store
+// The code is written against a tiny "platform" layer (WVB_DEV, ld_u32, SMEM accessor) so that
+// tests/emul can compile the very same decode function for the host and run it without a GPU.
+// That emulation is a test harness only; the shipped library contains the CUDA instantiation only.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/wvb.h"
+#include "wv_tables.h"
+
+#ifdef __CUDACC__
+#define WVB_DEV __device__ __forceinline__
+#define WVB_DEV_NOINLINE __device__ __noinline__
+#define WVB_TABLE __device__ const
+static __device__ __forceinline__ uint32_t wvb_ld_u32(const uint8_t *p) { return __ldg((const uint32_t *)p); }
+static __device__ __forceinline__ uint8_t wvb_ld_u8(const uint8_t *p) { return __ldg(p); }
+static __device__ __forceinline__ int wvb_ffs(uint32_t x) { return __ffs((int)x); }
+static __device__ __forceinline__ int wvb_clz(uint32_t x) { return __clz((int)x); }
+#else
+#include <string.h>
+#define WVB_DEV inline
+#define WVB_DEV_NOINLINE inline
+#define WVB_TABLE static const
+static inline uint32_t wvb_ld_u32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static inline uint8_t wvb_ld_u8(const uint8_t *p) { return *p; }
+static inline int wvb_ffs(uint32_t x) { return x ? __builtin_ctz(x) + 1 : 0; }
+static inline int wvb_clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
+#endif
+
+namespace wvb {
+
+WVB_TABLE uint8_t k_log2[256] = WV_LOG2_TABLE_INIT;
+WVB_TABLE uint8_t k_exp2[256] = WV_EXP2_TABLE_INIT;
+
+enum : uint32_t {
+    F_BYTES_STORED = 3, F_MONO = 4, F_HYBRID = 8, F_JOINT = 0x10, F_FLOAT = 0x80, F_INT32 = 0x100, F_HYB_BITRATE = 0x200,
+    F_HYB_BALANCE = 0x400, F_FALSE_STEREO = 0x40000000u, F_DSD = 0x80000000u
+};
+
+// ---- format math ----------------------------------------------------------------------------
+WVB_DEV int exp2s(int log) // WordsUtils.cs:633-646 (long shifts, count masked to 6 bits)
+{
+    const bool neg = log < 0;
+    if (neg) log = -log;
+    const uint64_t value = (uint64_t)(k_exp2[log & 0xff] | 0x100);
+    const int sh = log >> 8;
+    const int r = sh <= 9 ? (int)(value >> (9 - sh)) : (int)(value << ((sh - 9) & 63));
+    return neg ? -r : r;
+}
+
+WVB_DEV int mylog2(uint32_t v32) // WordsUtils.cs:588-608, for 0 <= value < 2^32
+{
+    uint64_t v = (uint64_t)v32 + (v32 >> 9);
+    if (v < 256) {
+        const int dbits = 32 - wvb_clz((uint32_t)v);
+        return (dbits << 8) + k_log2[(uint32_t)(v << (9 - dbits)) & 0xff];
+    }
+    const int dbits = v >> 32 ? 33 : 32 - wvb_clz((uint32_t)v);
+    return (dbits << 8) + k_log2[(uint32_t)(v >> (dbits - 9)) & 0xff];
+}
+
+WVB_DEV int restore_weight(int w8) // WordsUtils.cs:653-661, w8 already sign-extended from sbyte
+{
+    int r = w8 << 3;
+    if (r > 0) r += (r + 64) >> 7;
+    return r;
+}
+
+// ---- bit reader ------------------------------------------------------------------------------
+// LSB-first reader over [start, start+len); every bit past the end reads as 1 (the reference floods its
+// buffer with 0xFF on overrun, BitsUtils.cs:132-146).  A plain LSB-first window is bit-identical to
+// getbit/getbits.
+struct BitReader {
+    const uint8_t *next; // 4-byte aligned address of the next word
+    const uint8_t *end;
+    uint64_t bb;
+    int bc;
+
+    WVB_DEV uint32_t load_word()
+    {
+        uint32_t x;
+        if (next + 4 <= end) x = wvb_ld_u32(next);
+        else if (next >= end) x = 0xFFFFFFFFu;
+        else x = wvb_ld_u32(next) | (0xFFFFFFFFu << (8 * (int)(end - next)));
+        next += 4;
+        return x;
+    }
+    WVB_DEV void init(const uint8_t *s, uint32_t len)
+    {
+        end = s + len;
+        const int mis = (int)((uintptr_t)s & 3);
+        next = s - mis;
+        const uint32_t x = load_word();
+        bb = x >> (8 * mis);
+        bc = 32 - 8 * mis;
+    }
+    WVB_DEV void refill()
+    {
+        if (bc <= 32) {
+            bb |= (uint64_t)load_word() << bc;
+            bc += 32;
+        }
+    }
+    WVB_DEV void consume(int n) { bb >>= n; bc -= n; }
+    WVB_DEV uint32_t peek() const { return (uint32_t)bb; }
+    WVB_DEV uint32_t getbit() { refill(); const uint32_t b = (uint32_t)bb & 1u; consume(1); return b; }
+    WVB_DEV uint32_t getbits(int n) // 0 <= n <= 32
+    {
+        refill();
+        const uint32_t v = n >= 32 ? (uint32_t)bb : ((uint32_t)bb & ((1u << n) - 1u));
+        consume(n);
+        return v;
+    }
+};
+
+// ---- entropy decoder state (words_data.cs / entropy_data.cs) ---------------------------------
+template <bool HYB> struct Words;
+template <> struct Words<false> {
+    int m[2][3];
+    int hold; // 0 none, 1 holding_one, 2 holding_zero
+    uint32_t zeros_acc;
+};
+template <> struct Words<true> {
+    int m[2][3];
+    int hold;
+    uint32_t zeros_acc;
+    int slow[2], errlim[2];
+    int64_t bacc[2], bdelta[2];
+};
+
+template <bool STEREO> WVB_DEV void update_error_limit(Words<true> &w, uint32_t flags) // WordsUtils.cs:195-261
+{
+    int b0 = (int)((w.bacc[0] += w.bdelta[0]) >> 16);
+    if (!STEREO) {
+        if (flags & F_HYB_BITRATE) {
+            const int sl0 = (w.slow[0] + 128) >> 8;
+            w.errlim[0] = sl0 - b0 > -0x100 ? exp2s(sl0 - b0 + 0x100) : 0;
+        } else
+            w.errlim[0] = exp2s(b0);
+    } else {
+        int b1 = (int)((w.bacc[1] += w.bdelta[1]) >> 16);
+        if (flags & F_HYB_BITRATE) {
+            const int sl0 = (w.slow[0] + 128) >> 8, sl1 = (w.slow[1] + 128) >> 8;
+            if (flags & F_HYB_BALANCE) {
+                const int balance = (sl1 - sl0 + b1 + 1) >> 1;
+                if (balance > b0) { b1 = b0 * 2; b0 = 0; }
+                else if (-balance > b0) { b0 = b0 * 2; b1 = 0; }
+                else { b1 = b0 + balance; b0 = b0 - balance; }
+            }
+            w.errlim[0] = sl0 - b0 > -0x100 ? exp2s(sl0 - b0 + 0x100) : 0;
+            w.errlim[1] = sl1 - b1 > -0x100 ? exp2s(sl1 - b1 + 0x100) : 0;
+        } else {
+            w.errlim[0] = exp2s(b0);
+            w.errlim[1] = exp2s(b1);
+        }
+    }
+}
+
+// gamma-style count shared by the zero-run and the unary escape (WordsUtils.cs:321-335, 391-405).
+// returns false on the 33-ones EOF.
+WVB_DEV bool read_gamma(BitReader &br, uint32_t &value)
+{
+    int cbits = 0;
+    while (cbits < 33 && br.getbit()) ++cbits;
+    if (cbits == 33) return false;
+    if (cbits < 2) { value = (uint32_t)cbits; return true; }
+    uint32_t mask = 1, acc = 0;
+    for (; --cbits > 0; mask <<= 1)
+        if (br.getbit()) acc |= mask;
+    value = acc | mask;
+    return true;
+}
+
+// read_code for ranges >= 2^30, where the reference's int/long mixing matters (WordsUtils.cs:546-570, quirk C-3)
+WVB_DEV_NOINLINE uint32_t read_code_wide(BitReader &br, uint32_t low, uint32_t range)
+{
+    const int bitcount = 32 - wvb_clz(range);
+    const int64_t extras = (int64_t)(int32_t)(1u << (bitcount & 31)) - (int64_t)range - 1;
+    int64_t code = (int64_t)br.getbits(bitcount - 1);
+    code &= (int64_t)(int32_t)((1u << ((bitcount - 1) & 31)) - 1u);
+    if (code >= extras) {
+        code = (code << 1) - extras;
+        if (br.getbit()) ++code;
+    }
+    return (uint32_t)((int64_t)low + code);
+}
+
+// One word of get_words for channel CH.  Returns false when the reference would `break` (EOF / error).
+template <bool HYB, bool STEREO, int CH> WVB_DEV bool decode_word(BitReader &br, Words<HYB> &w, uint32_t flags, int &out)
+{
+    int *med = w.m[CH];
+    if (((w.m[0][0] | w.m[1][0]) & ~1) == 0 && w.hold == 0) { // WordsUtils.cs:304-352
+        if (w.zeros_acc > 0) {
+            if (--w.zeros_acc > 0) {
+                if constexpr (HYB) w.slow[CH] -= (w.slow[CH] + 128) >> 8;
+                out = 0;
+                return true;
+            }
+        } else {
+            uint32_t z;
+            if (!read_gamma(br, z)) return false;
+            w.zeros_acc = z;
+            if (z > 0) {
+                if constexpr (HYB) w.slow[CH] -= (w.slow[CH] + 128) >> 8;
+                w.m[0][0] = w.m[0][1] = w.m[0][2] = 0;
+                w.m[1][0] = w.m[1][1] = w.m[1][2] = 0;
+                out = 0;
+                return true;
+            }
+        }
+    }
+
+    br.refill(); // >= 33 bits
+    int ones;
+    if (w.hold == 2) { // WordsUtils.cs:354-358
+        w.hold = 0;
+        ones = 0;
+    } else { // WordsUtils.cs:361-428
+        int t = wvb_ffs(~br.peek()) - 1;
+        if ((unsigned)t >= 16u) {
+            br.consume(16);
+            if (br.getbit()) return false; // 17 ones: end of stream
+            uint32_t v;
+            if (!read_gamma(br, v)) return false;
+            t = (int)v + 16;
+            br.refill();
+        } else
+            br.consume(t + 1);
+        const int h1 = w.hold == 1;
+        w.hold = (t & 1) ? 1 : 2;
+        ones = (t >> 1) + h1;
+    }
+
+    if constexpr (HYB && CH == 0) update_error_limit<STEREO>(w, flags); // WordsUtils.cs:430-431
+
+    uint32_t low, high; // WordsUtils.cs:433-475
+    {
+        const int g0 = (med[0] >> 4) + 1;
+        if (ones == 0) {
+            low = 0;
+            high = (uint32_t)g0 - 1;
+            med[0] -= ((med[0] + 126) >> 7) * 2;
+        } else {
+            low = (uint32_t)g0;
+            med[0] += ((med[0] + 128) >> 7) * 5;
+            const int g1 = (med[1] >> 4) + 1;
+            if (ones == 1) {
+                high = low + (uint32_t)g1 - 1;
+                med[1] -= ((med[1] + 62) >> 6) * 2;
+            } else {
+                low += (uint32_t)g1;
+                med[1] += ((med[1] + 64) >> 6) * 5;
+                const int g2 = (med[2] >> 4) + 1;
+                if (ones == 2) {
+                    high = low + (uint32_t)g2 - 1;
+                    med[2] -= ((med[2] + 30) >> 5) * 2;
+                } else {
+                    low += (uint32_t)((ones - 2) * g2);
+                    high = low + (uint32_t)g2 - 1;
+                    med[2] += ((med[2] + 32) >> 5) * 5;
+                }
+            }
+        }
+    }
+
+    uint32_t mid;
+    bool lossless_code = true;
+    if constexpr (HYB) lossless_code = w.errlim[CH] == 0;
+    if (lossless_code) { // read_code, WordsUtils.cs:546-570
+        const uint32_t range = high - low;
+        uint32_t code = 0;
+        if (range) {
+            const int bitcount = 32 - wvb_clz(range);
+            if (bitcount >= 31) {
+                mid = read_code_wide(br, low, range);
+                goto have_mid;
+            }
+            const uint32_t extras = (1u << bitcount) - range - 1u;
+            br.refill();
+            code = br.peek() & ((1u << (bitcount - 1)) - 1u);
+            br.consume(bitcount - 1);
+            if (code >= extras) {
+                code = (code << 1) - extras + (br.peek() & 1u);
+                br.consume(1);
+            }
+        }
+        mid = low + code;
+    } else if constexpr (HYB) { // WordsUtils.cs:477-492
+        const uint32_t lim = (uint32_t)w.errlim[CH];
+        mid = (uint32_t)(((uint64_t)high + low + 1) >> 1);
+        while (high - low > lim) {
+            if (br.getbit()) low = mid;
+            else high = mid - 1;
+            mid = (uint32_t)(((uint64_t)high + low + 1) >> 1);
+        }
+    }
+have_mid:
+    br.refill();
+    out = (br.peek() & 1u) ? (int)~mid : (int)mid; // WordsUtils.cs:494-497
+    br.consume(1);
+    if constexpr (HYB) {
+        if (flags & F_HYB_BITRATE) // WordsUtils.cs:501-502
+            w.slow[CH] = w.slow[CH] - ((w.slow[CH] + 128) >> 8) + mylog2(mid);
+    }
+    return true;
+}
+
+// ---- decorrelation ---------------------------------------------------------------------------
+WVB_DEV int apply_weight(int w, int s) { return (int)(((int64_t)w * (int64_t)s + 512) >> 10); }
+WVB_DEV int upd_weight(int w, int delta, int s, int in) // UnpackUtils.cs:707-713
+{
+    if (s != 0 && in != 0) w += ((s ^ in) < 0) ? -delta : delta;
+    return w;
+}
+WVB_DEV int upd_weight_clip(int w, int delta, int s, int in) // UnpackUtils.cs:776-785
+{
+    if (s != 0 && in != 0) {
+        if ((s ^ in) < 0) { w -= delta; if (w < -1024) w = -1024; }
+        else { w += delta; if (w > 1024) w = 1024; }
+    }
+    return w;
+}
+
+// pass descriptor word: term+5 [0..4], delta [5..7], ring mask [8..10], slot base [16..31]
+WVB_DEV uint32_t pack_pass(int term, int delta, int mask, int base) { return (uint32_t)(term + 5) | ((uint32_t)delta << 5) | ((uint32_t)mask << 8) | ((uint32_t)base << 16); }
+WVB_DEV int ring_mask(int term) { return term > 8 ? 1 : term < 0 ? 0 : term <= 1 ? 0 : term <= 2 ? 1 : term <= 4 ? 3 : 7; }
+
+// SM(i): word i of this thread's private shared-memory column
+template <bool STEREO, class SMEM> WVB_DEV void decorr_frame(SMEM &SM, int nterms, uint32_t t, int &a, int &b)
+{
+    for (int p = 0; p < nterms; ++p) {
+        const uint32_t d = (uint32_t)SM(p);
+        const int term = (int)(d & 31u) - 5, delta = (int)((d >> 5) & 7u), mask = (int)((d >> 8) & 7u), base = (int)(d >> 16);
+        if (STEREO) {
+            int wA = SM(base), wB = SM(base + 1);
+            const int hb = base + 2;
+            if (term > 8) { // 17 / 18: UnpackUtils.cs:700-768, 958-1008
+                const int i0 = hb + (int)((t - 1) & 1u), i1 = hb + (int)(t & 1u);
+                int h0 = SM(i0), h1 = SM(i1);
+                int s = term == 17 ? 2 * h0 - h1 : (3 * h0 - h1) >> 1;
+                const int oa = a + apply_weight(wA, s);
+                wA = upd_weight(wA, delta, s, a);
+                SM(i1) = oa;
+                h0 = SM(i0 + 2); h1 = SM(i1 + 2);
+                s = term == 17 ? 2 * h0 - h1 : (3 * h0 - h1) >> 1;
+                const int ob = b + apply_weight(wB, s);
+                wB = upd_weight(wB, delta, s, b);
+                SM(i1 + 2) = ob;
+                a = oa; b = ob;
+            } else if (term > 0) { // 1..8: UnpackUtils.cs:885-938, 1119-1148
+                const int ir = hb + (int)((t - (uint32_t)term) & (uint32_t)mask), iw = hb + (int)(t & (uint32_t)mask);
+                int s = SM(ir);
+                const int oa = a + apply_weight(wA, s);
+                wA = upd_weight(wA, delta, s, a);
+                SM(iw) = oa;
+                s = SM(ir + mask + 1);
+                const int ob = b + apply_weight(wB, s);
+                wB = upd_weight(wB, delta, s, b);
+                SM(iw + mask + 1) = ob;
+                a = oa; b = ob;
+            } else if (term == -1) { // UnpackUtils.cs:771-804, 1011-1042
+                const int s = SM(hb);
+                const int oa = a + apply_weight(wA, s);
+                wA = upd_weight_clip(wA, delta, s, a);
+                const int ob = b + apply_weight(wB, oa);
+                wB = upd_weight_clip(wB, delta, oa, b);
+                SM(hb) = ob;
+                a = oa; b = ob;
+            } else if (term == -2) { // UnpackUtils.cs:807-843, 1045-1080
+                const int s = SM(hb);
+                const int ob = b + apply_weight(wB, s);
+                wB = upd_weight_clip(wB, delta, s, b);
+                const int oa = a + apply_weight(wA, ob);
+                wA = upd_weight_clip(wA, delta, ob, a);
+                SM(hb) = oa;
+                a = oa; b = ob;
+            } else { // -3: UnpackUtils.cs:846-882, 1083-1116
+                const int sA = SM(hb), sB = SM(hb + 1);
+                const int oa = a + apply_weight(wA, sA);
+                wA = upd_weight_clip(wA, delta, sA, a);
+                const int ob = b + apply_weight(wB, sB);
+                wB = upd_weight_clip(wB, delta, sB, b);
+                SM(hb) = ob;     // samples_A[0] = B output
+                SM(hb + 1) = oa; // samples_B[0] = A output
+                a = oa; b = ob;
+            }
+            SM(base) = wA;
+            SM(base + 1) = wB;
+        } else { // decorr_mono_pass, UnpackUtils.cs:1156-1240 (negative terms already folded to term & 7 at init)
+            int wA = SM(base);
+            const int hb = base + 1;
+            int s, iw;
+            if (term > 8) {
+                const int i0 = hb + (int)((t - 1) & 1u);
+                iw = hb + (int)(t & 1u);
+                const int h0 = SM(i0), h1 = SM(iw);
+                s = term == 17 ? 2 * h0 - h1 : (3 * h0 - h1) >> 1;
+            } else {
+                const int ir = hb + (int)((t - (uint32_t)term) & (uint32_t)mask);
+                iw = hb + (int)(t & (uint32_t)mask);
+                s = SM(ir);
+            }
+            const int oa = a + apply_weight(wA, s);
+            wA = upd_weight(wA, delta, s, a);
+            SM(iw) = oa;
+            SM(base) = wA;
+            a = oa;
+        }
+    }
+}
+
+template <bool STEREO, class SMEM> WVB_DEV void truncate_weights(SMEM &SM, int nterms) // (short) casts at UnpackUtils.cs:942-943,1152-1153,1239
+{
+    for (int p = 0; p < nterms; ++p) {
+        const int base = (int)((uint32_t)SM(p) >> 16);
+        SM(base) = (int)(int16_t)SM(base);
+        if (STEREO) SM(base + 1) = (int)(int16_t)SM(base + 1);
+    }
+}
+
+// ---- fixup (UnpackUtils.cs:1251-1404, FloatUtils.cs:32-56) -----------------------------------
+struct Fixup {
+    int mode;  // 0 shift only, 1 float, 2 int32+wvx, 3 int32 redundancy only (no wvx)
+    int shift; // final shift (already & 0x1f)
+    int lossy;
+    int minv, maxv, mins, maxs;
+    int sent, zeros, ones, dups, max_width;
+    int fshift; // float shift in [-32, 32]
+};
+
+WVB_DEV int shl32(int v, int n) { return (int)((uint32_t)v << (n & 31)); }
+
+WVB_DEV void fixup_init(Fixup &f, uint32_t flags, const uint8_t *int32_info, const uint8_t *float_info, bool wvx_present, int max_width)
+{
+    f.mode = 0;
+    f.lossy = (flags & F_HYBRID) != 0;
+    int shift = (int)((flags >> 13) & 0x1f);
+    f.sent = f.zeros = f.ones = f.dups = 0;
+    f.max_width = max_width;
+    f.fshift = 0;
+    if (flags & F_FLOAT) {
+        int s = (int)float_info[2] - (int)float_info[3] + (int)float_info[1];
+        f.fshift = s > 32 ? 32 : s < -32 ? -32 : s;
+        f.mode = 1;
+    } else if (flags & F_INT32) {
+        int sent = int32_info[0], zeros = int32_info[1], ones = int32_info[2], dups = int32_info[3];
+        if (wvx_present) {
+            f.mode = 2;
+            f.sent = sent; f.zeros = zeros; f.ones = ones; f.dups = dups;
+        } else if (sent == 0 && (zeros + ones + dups) != 0) {
+            while (f.lossy && (flags & F_BYTES_STORED) == 3 && shift < 8) {
+                if (zeros > 0) zeros--;
+                else if (ones > 0) ones--;
+                else if (dups > 0) dups--;
+                else break;
+                shift++;
+            }
+            f.mode = 3;
+            f.zeros = zeros; f.ones = ones; f.dups = dups;
+        } else
+            shift += zeros + sent + ones + dups;
+    }
+    shift &= 0x1f;
+    f.shift = shift;
+    f.minv = f.maxv = f.mins = f.maxs = 0;
+    if (f.lossy) {
+        switch (flags & F_BYTES_STORED) {
+        case 0: f.minv = -128 >> shift; f.maxv = 127 >> shift; break;
+        case 1: f.minv = -32768 >> shift; f.maxv = 32767 >> shift; break;
+        case 2: f.minv = -8388608 >> shift; f.maxv = 8388607 >> shift; break;
+        default: f.minv = (int)(0x80000000u >> shift); f.maxv = 0x7FFFFFFF >> shift; break; // quirk C-7
+        }
+        f.mins = shl32(f.minv, shift);
+        f.maxs = shl32(f.maxv, shift);
+    }
+}
+
+WVB_DEV int fixup_redundancy(const Fixup &f, int v)
+{
+    if (f.zeros != 0) v = shl32(v, f.zeros);
+    else if (f.ones != 0) v = shl32(v + 1, f.ones) - 1;
+    else if (f.dups != 0) v = shl32(v + (v & 1), f.dups) - (v & 1);
+    return v;
+}
+
+WVB_DEV int fixup_value(const Fixup &f, int v, BitReader &wvx, int &crc_x)
+{
+    if (f.mode == 1) {
+        if (f.fshift > 0) v = shl32(v, f.fshift);
+        else if (f.fshift < 0) v = v >> ((-f.fshift) & 31);
+        return v > 8388607 ? 8388607 : v < -8388608 ? -8388608 : v;
+    }
+    if (f.mode == 2) {
+        const uint32_t mask = (f.sent & 31) ? ((1u << (f.sent & 31)) - 1u) : 0u; // (1U << sent_bits) - 1 with a masked count
+        if (f.sent > 0) {
+            if (f.max_width > 0) {
+                const int pv = v < 0 ? ~v : v;
+                const int width = (32 - wvb_clz((uint32_t)pv)) + f.sent;
+                int btr = f.sent;
+                if (width <= f.max_width || (btr -= width - f.max_width) > 0) {
+                    const uint32_t data = wvx.getbits(btr > 32 ? 32 : btr) & mask;
+                    v = shl32((int)((uint32_t)shl32(v, btr) | data), f.sent - btr);
+                } else
+                    v = shl32(v, f.sent);
+            } else {
+                const uint32_t data = wvx.getbits(f.sent > 32 ? 32 : f.sent) & mask;
+                v = (int)(((uint32_t)v << (f.sent & 31)) | data);
+            }
+        }
+        v = fixup_redundancy(f, v);
+        crc_x = crc_x * 9 + (v & 0xffff) * 3 + ((v >> 16) & 0xffff);
+    } else if (f.mode == 3)
+        v = fixup_redundancy(f, v);
+    if (f.lossy) return v < f.minv ? f.mins : v > f.maxv ? f.maxs : shl32(v, f.shift);
+    return shl32(v, f.shift);
+}
+
+// ---- output ----------------------------------------------------------------------------------
+WVB_DEV void store_unit(uint8_t *q, int v, int unit, int add128)
+{
+    if (unit == 4) *(int *)q = v;
+    else if (unit == 2) *(uint16_t *)q = (uint16_t)v;
+    else if (unit == 3) { q[0] = (uint8_t)v; q[1] = (uint8_t)(v >> 8); q[2] = (uint8_t)(v >> 16); }
+    else q[0] = (uint8_t)(v + add128);
+}
+
+// ---- the per-thread block decoder ------------------------------------------------------------
+// STEREO: two coded channels (neither MONO_FLAG nor FALSE_STEREO).  HYB: HYBRID_FLAG.  GENFIX: float / int32 / hybrid fixup.
+template <bool STEREO, bool HYB, bool GENFIX, class SMEM>
+WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc &D, uint8_t *out, int out_format, wvb_block_result *res)
+{
+    const uint8_t *blk = in + D.in_offset;
+    const uint32_t flags = D.flags;
+    const uint32_t n = D.block_samples;
+    const int unit = out_format == WVB_OUT_INT32 ? 4 : (int)D.out_bps;
+    const int add128 = (out_format == WVB_OUT_PCM && unit == 1) ? 128 : 0;
+    const uint32_t frame_bytes = (uint32_t)unit * D.out_stride;
+    const int out_ch = D.out_channels;
+    uint8_t *op = out + D.out_offset + (uint32_t)unit * D.out_ch_offset;
+    uint32_t rflags = 0;
+
+    if (D.gap_before) { // zero fill before the block (WavPackUtils.cs:227-251)
+        uint8_t *g = out + D.out_offset - (uint64_t)D.gap_before * frame_bytes;
+        for (uint32_t i = 0; i < D.gap_before; ++i, g += frame_bytes)
+            for (int c = 0; c < D.out_stride; ++c) store_unit(g + c * unit, 0, unit, add128);
+    }
+    if (D.bflags & WVB_BF_MUTE_ALL) {
+        for (uint32_t i = 0; i < n; ++i, op += frame_bytes)
+            for (int c = 0; c < out_ch; ++c) store_unit(op + c * unit, 0, unit, add128);
+        res->crc = -1; res->crc_x = -1; res->mute_from = 0;
+        res->rflags = WVB_RF_MUTED | WVB_RF_CRC_ERROR | WVB_RF_INEXACT;
+        return;
+    }
+    if (D.bflags & WVB_BF_STALE_STATE) rflags |= WVB_RF_INEXACT;
+
+    // ---- metadata contents -> state ----
+    const int nterms = (int)D.sub_len[WVB_SUB_TERMS];
+    {
+        const uint8_t *tp = blk + D.sub_off[WVB_SUB_TERMS];
+        int base = nterms;
+        for (int d = 0; d < nterms; ++d) { // decoder order d <-> file byte nterms-1-d (UnpackUtils.cs:170-181)
+            const uint8_t tb = wvb_ld_u8(tp + (nterms - 1 - d));
+            int term = (int)(tb & 0x1f) - 5;
+            const int delta = (tb >> 5) & 7;
+            if (!STEREO && term < 0) term &= 7; // decorr_mono_pass default branch (UnpackUtils.cs:1207)
+            const int mask = ring_mask(term);
+            SM(d) = (int)pack_pass(term, delta, mask, base);
+            const int words = STEREO ? 2 + 2 * (mask + 1) : 1 + (mask + 1);
+            for (int k = 0; k < words; ++k) SM(base + k) = 0;
+            base += words;
+        }
+        // weights (UnpackUtils.cs:196-239): file order walks decoder index nterms-1 downwards
+        const uint8_t *wp = blk + D.sub_off[WVB_SUB_WEIGHTS];
+        int cnt = (int)D.sub_len[WVB_SUB_WEIGHTS];
+        if (STEREO) cnt >>= 1;
+        for (int j = 0; j < cnt; ++j) {
+            const int d = nterms - 1 - j;
+            const int b0 = (int)((uint32_t)SM(d) >> 16);
+            if (STEREO) {
+                SM(b0) = (int)(int16_t)restore_weight((int8_t)wvb_ld_u8(wp + 2 * j));
+                SM(b0 + 1) = (int)(int16_t)restore_weight((int8_t)wvb_ld_u8(wp + 2 * j + 1));
+            } else
+                SM(b0) = (int)(int16_t)restore_weight((int8_t)wvb_ld_u8(wp + j));
+        }
+        // history (UnpackUtils.cs:250-360) incl. quirk C-1: every entry is parsed with the term of pass nterms-1
+        const uint8_t *sp = blk + D.sub_off[WVB_SUB_SAMPLES];
+        const int slen = (int)D.sub_len[WVB_SUB_SAMPLES];
+        if (slen > 0 && nterms > 0) {
+            const int qterm = (int)(wvb_ld_u8(tp) & 0x1f) - 5; // raw term of decorr_passes[nterms-1] = first file byte
+            int counter = 0;
+            if (D.version == 0x402 && (flags & F_HYBRID)) counter += STEREO ? 4 : 2;
+            int d = nterms - 1;
+            int sA[8], sB[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sA[k] = sB[k] = 0;
+            while (counter < slen && d >= 0) {
+#define RD16S(at) exp2s((int)(int16_t)((uint32_t)wvb_ld_u8(sp + (at)) | ((uint32_t)wvb_ld_u8(sp + (at) + 1) << 8)))
+                if (qterm > 8) {
+                    sA[0] = RD16S(counter); sA[1] = RD16S(counter + 2); counter += 4;
+                    if (STEREO) { sB[0] = RD16S(counter); sB[1] = RD16S(counter + 2); counter += 4; }
+                } else if (qterm < 0) {
+                    sA[0] = RD16S(counter); sB[0] = RD16S(counter + 2); counter += 4;
+                } else {
+#pragma unroll
+                    for (int m = 0; m < 8; ++m)
+                        if (m < qterm) {
+                            sA[m] = RD16S(counter); counter += 2;
+                            if (STEREO) { sB[m] = RD16S(counter); counter += 2; }
+                        }
+                }
+#undef RD16S
+                // place the reference's samples_A/B[] image into this pass's ring according to ITS term
+                const uint32_t dd = (uint32_t)SM(d);
+                const int term = (int)(dd & 31u) - 5, mask = (int)((dd >> 8) & 7u), base0 = (int)(dd >> 16);
+                const int hb = base0 + (STEREO ? 2 : 1);
+                if (term > 8) {
+                    SM(hb + 1) = sA[0]; SM(hb + 0) = sA[1]; // x[-1] -> slot 1, x[-2] -> slot 0
+                    if (STEREO) { SM(hb + 3) = sB[0]; SM(hb + 2) = sB[1]; }
+                } else if (term > 0) {
+#pragma unroll
+                    for (int m = 0; m < 8; ++m)
+                        if (m < term) { // samples[m] = x[-term+m]
+                            SM(hb + ((m - term) & mask)) = sA[m];
+                            if (STEREO) SM(hb + mask + 1 + ((m - term) & mask)) = sB[m];
+                        }
+                } else if (term == -1) SM(hb) = sA[0];
+                else if (term == -2) SM(hb) = sB[0];
+                else { SM(hb) = sA[0]; SM(hb + 1) = sB[0]; }
+                --d;
+            }
+        }
+    }
+
+    Words<HYB> w;
+    {
+        const uint8_t *ep = blk + D.sub_off[WVB_SUB_ENTROPY];
+#define RD16U(p, at) ((int)((uint32_t)wvb_ld_u8((p) + (at)) | ((uint32_t)wvb_ld_u8((p) + (at) + 1) << 8)))
+        w.m[0][0] = exp2s(RD16U(ep, 0)); w.m[0][1] = exp2s(RD16U(ep, 2)); w.m[0][2] = exp2s(RD16U(ep, 4));
+        if (STEREO) { w.m[1][0] = exp2s(RD16U(ep, 6)); w.m[1][1] = exp2s(RD16U(ep, 8)); w.m[1][2] = exp2s(RD16U(ep, 10)); }
+        else w.m[1][0] = w.m[1][1] = w.m[1][2] = 0;
+        w.hold = 0;
+        w.zeros_acc = 0;
+        if constexpr (HYB) { // read_hybrid_profile, WordsUtils.cs:124-187
+            Words<true> &h = w;
+            h.slow[0] = h.slow[1] = 0; h.errlim[0] = h.errlim[1] = 0;
+            h.bacc[0] = h.bacc[1] = 0; h.bdelta[0] = h.bdelta[1] = 0;
+            const uint8_t *hp = blk + D.sub_off[WVB_SUB_HYBRID];
+            const int hl = D.sub_off[WVB_SUB_HYBRID] ? (int)D.sub_len[WVB_SUB_HYBRID] : 0;
+            if (D.sub_off[WVB_SUB_HYBRID]) {
+                int k = 0;
+                if (flags & F_HYB_BITRATE) {
+                    h.slow[0] = exp2s(RD16U(hp, k)); k += 2;
+                    if (STEREO) { h.slow[1] = exp2s(RD16U(hp, k)); k += 2; }
+                }
+                h.bacc[0] = (int64_t)(int32_t)((uint32_t)RD16U(hp, k) << 16); k += 2;
+                if (STEREO) { h.bacc[1] = (int64_t)(int32_t)((uint32_t)RD16U(hp, k) << 16); k += 2; }
+                if (k < hl) {
+                    h.bdelta[0] = exp2s((int)(int16_t)RD16U(hp, k)); k += 2;
+                    if (STEREO) { h.bdelta[1] = exp2s((int)(int16_t)RD16U(hp, k)); k += 2; }
+                }
+            }
+        }
+#undef RD16U
+    }
+
+    BitReader br;
+    br.init(blk + D.sub_off[WVB_SUB_WV], D.sub_len[WVB_SUB_WV]);
+
+    Fixup fx;
+    BitReader wvx;
+    int crc_x = -1, crc_mvx = 0;
+    bool wvx_here = false;
+    if (GENFIX) {
+        int max_width = 0;
+        wvx_here = (D.bflags & WVB_BF_WVX_PRESENT) && D.sub_off[WVB_SUB_WVX];
+        if (wvx_here) { // init_wvx_bitstream, UnpackUtils.cs:115-147
+            const uint8_t *xp = blk + D.sub_off[WVB_SUB_WVX];
+            crc_mvx = (int)((uint32_t)wvb_ld_u8(xp) | ((uint32_t)wvb_ld_u8(xp + 1) << 8) | ((uint32_t)wvb_ld_u8(xp + 2) << 16) |
+                            ((uint32_t)wvb_ld_u8(xp + 3) << 24));
+            wvx.init(xp + 4, D.sub_len[WVB_SUB_WVX] - 4);
+            if (D.bflags & WVB_BF_WVX_NEW) {
+                if (flags & F_FLOAT) { wvx.getbits(5); wvx.getbits(5); }
+                else max_width = (int)(wvx.getbits(5) & 0x1f);
+            }
+        } else
+            wvx.init(blk, 0);
+        fixup_init(fx, flags, D.int32_info, D.float_info, (D.bflags & WVB_BF_WVX_PRESENT) != 0, max_width);
+        if ((flags & F_INT32) && (D.bflags & WVB_BF_WVX_PRESENT) && (flags & F_FALSE_STEREO)) rflags |= WVB_RF_INEXACT; // quirk C-6
+    } else {
+        fx.shift = (int)((flags >> 13) & 0x1f);
+    }
+
+    int mute_limit = (int)((1LL << ((flags >> 18) & 0x1f)) + 2); // UnpackUtils.cs:517
+    if (flags & F_HYBRID) mute_limit *= 2;
+    const bool joint = STEREO && (flags & F_JOINT);
+    const int fast16 = (!GENFIX && STEREO && out_format == WVB_OUT_PCM && unit == 2 && D.out_stride == 2 && D.out_ch_offset == 0) ? 1 : 0;
+
+    // call/chunk grid (weights are cast to short at the end of every pass call: after the first 8 samples of a
+    // stereo piece of >= 16 samples and at the end of the piece)
+    const uint32_t chunk = D.chunk_samples ? D.chunk_samples : 0xffffffffu;
+    uint32_t piece_start = 0;
+    uint32_t piece_end = D.chunk_first < n ? D.chunk_first : n;
+    if (piece_end == 0) piece_end = chunk < n ? chunk : n;
+    uint32_t trunc8 = (STEREO && piece_end - piece_start >= 16) ? piece_start + 8 : 0xffffffffu;
+
+    int crc = -1;
+    uint32_t t = 0;
+    bool fault = false, eof_fault = false;
+    for (; t < n; ++t) {
+        if (t == piece_end) {
+            truncate_weights<STEREO>(SM, nterms);
+            piece_start = t;
+            const uint32_t rest = n - t;
+            piece_end = t + (chunk < rest ? chunk : rest);
+            trunc8 = (STEREO && piece_end - piece_start >= 16) ? piece_start + 8 : 0xffffffffu;
+        } else if (t == trunc8)
+            truncate_weights<STEREO>(SM, nterms);
+
+        int a, b = 0;
+        if (!decode_word<HYB, STEREO, 0>(br, w, flags, a)) { fault = eof_fault = true; break; }
+        if (STEREO && !decode_word<HYB, STEREO, 1>(br, w, flags, b)) { fault = eof_fault = true; break; }
+
+        decorr_frame<STEREO>(SM, nterms, t, a, b);
+
+        if (joint) { b -= (a >> 1); a += b; } // UnpackUtils.cs:615 (App. E-9)
+        {
+            const int aa = a < 0 ? -a : a, ab = b < 0 ? -b : b;
+            if (aa > mute_limit || (STEREO && ab > mute_limit)) { fault = true; break; }
+        }
+        crc = crc * 3 + a;
+        if (STEREO) crc = crc * 3 + b;
+
+        if (fast16) {
+            *(uint32_t *)op = ((uint32_t)shl32(a, fx.shift) & 0xffffu) | ((uint32_t)shl32(b, fx.shift) << 16);
+        } else {
+            int va, vb = 0;
+            if (GENFIX) {
+                va = fixup_value(fx, a, wvx, crc_x);
+                if (STEREO) vb = fixup_value(fx, b, wvx, crc_x);
+            } else {
+                va = shl32(a, fx.shift);
+                if (STEREO) vb = shl32(b, fx.shift);
+            }
+            store_unit(op, va, unit, add128);
+            if (out_ch == 2) store_unit(op + unit, STEREO ? vb : va, unit, add128); // FALSE_STEREO duplicates (UnpackUtils.cs:668-680)
+        }
+        op += frame_bytes;
+    }
+
+    if (fault) { // mute from the start of the caller chunk that contains the fault (UnpackUtils.cs:649-664, App. E-10)
+        rflags |= WVB_RF_MUTED;
+        uint8_t *q = out + D.out_offset + (uint32_t)unit * D.out_ch_offset + (uint64_t)piece_start * frame_bytes;
+        // the first muted chunk still runs through fixup_samples with zeros; only INT32 "ones" (and WVX data bits) make that non-zero
+        for (uint32_t i = piece_start; i < n; ++i, q += frame_bytes) {
+            int z = 0;
+            if (GENFIX && i < piece_end) {
+                if (fx.mode == 2 && fx.sent > 0) rflags |= WVB_RF_INEXACT;
+                if (fx.mode == 2 || fx.mode == 3) z = fixup_redundancy(fx, 0);
+                if (fx.mode != 1) z = fx.lossy ? (z < fx.minv ? fx.mins : z > fx.maxv ? fx.maxs : shl32(z, fx.shift)) : shl32(z, fx.shift);
+            }
+            for (int c = 0; c < out_ch; ++c) store_unit(q + c * unit, z, unit, add128);
+        }
+        res->mute_from = piece_start;
+    } else
+        res->mute_from = n;
+
+    // check_crc_error, UnpackUtils.cs:1414-1421
+    if (crc != D.crc || eof_fault) rflags |= WVB_RF_CRC_ERROR; // after a short get_words the reference's crc runs over stale buffer contents
+    if (GENFIX && !(flags & F_FLOAT) && (D.bflags & WVB_BF_WVX_PRESENT)) {
+        if (!wvx_here) rflags |= WVB_RF_INEXACT; // crc_mvx left over from an earlier block
+        else if (crc_x != crc_mvx) rflags |= WVB_RF_CRC_ERROR | WVB_RF_CRCX_ERROR;
+    }
+    res->crc = crc;
+    res->crc_x = crc_x;
+    res->rflags = rflags;
+}
+
+} // namespace wvb
