@@ -1,0 +1,406 @@
+#!/usr/bin/env python3
+"""bench.py -- batch WavPack decode throughput (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py --gpus 1 --steps K --warmup W                 # our arm (CUDA, libwvb.so)
+  python bench.py --impl reference --gpus N --steps K --warmup W  # reference arm: the reference's CPU decode path
+  torchrun --nproc-per-node N bench.py --gpus N ...             # one rank per GPU, no data-path collective
+
+Workload (config.workload): BASELINE.json configs[1] -- 10 000 synthetic 16-bit stereo 44.1 kHz default-mode
+.wv files of 10 s per GPU (weak scaling: every rank decodes its own 10 000 files; shards share nothing).
+A step = one decode pass over the whole batch.
+  value  : decoded complete samples/s, whole job, compressed input and PCM output resident in HBM
+  e2e    : same metric through the public C-ABI call with HOST (pinned) buffers: host index pass + H2D of the
+           compressed slab + kernels + D2H of the PCM, every step
+  roofline: algorithmic bytes (compressed block bytes in + PCM bytes out) / CUDA-event kernel time vs measured HBM peak
+  cpu_baseline: the oracle (C restatement of the reference, one file per thread on all host cores) on a bounded sample
+The C# reference cannot run in this image (no .NET); the reference arm therefore times the C restatement ("port").
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "decoded_samples_per_s"
+UNIT = "samples/s"
+
+
+def log(*a):
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(*a, file=sys.stderr, flush=True)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# --------------------------------------------------------------------------------------
+# synthetic corpus
+# --------------------------------------------------------------------------------------
+def build_corpus(nfiles, seconds, base_seed, threads, budget_s, pin):
+    """Encode up to `nfiles` unique files within ~budget_s (the rest are byte copies of earlier files placed at new
+    offsets; warps still hold 32 different blocks because replicas are nfiles_unique files apart)."""
+    import _harness as H
+    import torch
+    cfg = H.make_config()
+    n_per = int(cfg.sample_rate * seconds)
+    lib = H.wvenc()
+    # probe: size and speed
+    probe_n = max(2, min(threads, nfiles))
+    bound = lib.wvenc_bound(C.byref(cfg), n_per)
+    tmp = np.zeros(bound * probe_n, dtype=np.uint8)
+    offs = np.zeros(probe_n, dtype=np.uint64)
+    sizes = np.zeros(probe_n, dtype=np.uint64)
+    t0 = time.perf_counter()
+    used = lib.wvenc_build_corpus(C.byref(cfg), n_per, probe_n, base_seed, threads, tmp.ctypes.data, tmp.size, offs.ctypes.data, sizes.ctypes.data)
+    dt = time.perf_counter() - t0
+    assert used > 0
+    per_file = int(sizes.max())
+    rate = probe_n / dt
+    unique = int(max(probe_n, min(nfiles, rate * budget_s)))
+    slot = (int(per_file * 1.03) + 4096 + 63) & ~63
+    total_cap = slot * nfiles + 4096
+    slab_t = torch.empty(total_cap, dtype=torch.uint8, pin_memory=pin)
+    slab = slab_t.numpy()
+    offsets = np.zeros(nfiles, dtype=np.uint64)
+    fsizes = np.zeros(nfiles, dtype=np.uint64)
+    t0 = time.perf_counter()
+    used = lib.wvenc_build_corpus(C.byref(cfg), n_per, unique, base_seed, threads, slab.ctypes.data, slot * unique, offsets.ctypes.data, fsizes.ctypes.data)
+    assert used > 0, "corpus generation overflowed its slab"
+    gen_s = time.perf_counter() - t0
+    pos = (int(used) + 63) & ~63
+    for i in range(unique, nfiles):
+        j = i % unique
+        ln = int(fsizes[j])
+        o = int(offsets[j])
+        slab[pos:pos + ln] = slab[o:o + ln]
+        offsets[i] = pos
+        fsizes[i] = ln
+        pos += (ln + 63) & ~63
+    slab[pos:pos + 64] = 0
+    return dict(cfg=cfg, slab_t=slab_t, slab=slab[:pos + 64], slab_bytes=pos + 64, offsets=offsets, sizes=fsizes, unique=unique,
+                samples_per_file=n_per, gen_s=gen_s, compressed_bytes=int(fsizes.sum()))
+
+
+# --------------------------------------------------------------------------------------
+# CPU baseline: oracle (restated reference) over a bounded sample, one file per thread
+# --------------------------------------------------------------------------------------
+def cpu_decode_sample(corpus, nfiles_sample, threads):
+    import _harness as H
+    lib = H.refdec()
+    slab, offsets, sizes = corpus["slab"], corpus["offsets"], corpus["sizes"]
+    n_per = corpus["samples_per_file"]
+    pcm_cap = n_per * 4 + 64
+
+    def work(i):
+        buf = np.empty(pcm_cap, dtype=np.uint8)
+        ln = C.c_size_t()
+        errs = C.c_long()
+        n = lib.rd_decode_file_pcm(slab.ctypes.data + int(offsets[i]), int(sizes[i]), 0, 4096, buf.ctypes.data, pcm_cap, C.byref(ln), C.byref(errs))
+        return n, errs.value
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        res = list(ex.map(work, range(nfiles_sample)))
+    dt = time.perf_counter() - t0
+    samples = sum(r[0] for r in res)
+    assert all(r[1] == 0 for r in res)
+    return samples, dt
+
+
+def size_cpu_sample(corpus, threads, target_s):
+    """Pick a sample size so that the CPU leg takes about target_s."""
+    samples, dt = cpu_decode_sample(corpus, min(threads, len(corpus["offsets"])), threads)
+    rate = samples / dt
+    n = int(max(threads, min(len(corpus["offsets"]), rate * target_s / corpus["samples_per_file"])))
+    return n
+
+
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------------------
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    threads = host_cores()
+    nfiles = min(args.files, max(threads * 4, 64))
+    corpus = build_corpus(nfiles, args.seconds, 0x5EED0000, threads, args.gen_budget_s, pin=False)
+    n = size_cpu_sample(corpus, threads, args.cpu_baseline_s / max(1, (args.steps + args.warmup)))
+    n = max(threads, min(n, nfiles))
+    for _ in range(args.warmup):
+        cpu_decode_sample(corpus, n, threads)
+    t_total, s_total = 0.0, 0
+    for _ in range(args.steps):
+        s, dt = cpu_decode_sample(corpus, n, threads)
+        t_total += dt
+        s_total += s
+    value = s_total / t_total
+    sample = "%d of the workload's files (%d x %.0f s 16-bit stereo) per step, one file per thread" % (n, args.files, args.seconds)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic", "config": workload_config(args, corpus, None),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "C# reference cannot run here (no .NET runtime); this is its C restatement (oracle/refdec.c, -O2), decode + WavpackFormatSamples, inputs in memory",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, corpus, nblocks):
+    cfg = {
+        "workload": "BASELINE configs[1]: batch of %d synthetic 16-bit stereo 44.1 kHz default-mode .wv files x %.0f s per GPU, one WavPack block per thread" % (args.files, args.seconds),
+        "files_per_gpu": args.files, "seconds_per_file": args.seconds, "block_samples": 22050,
+        "unique_files_per_gpu": corpus["unique"] if corpus else None,
+        "l2_policy": "inputs (compressed slab + PCM output, GBs) far larger than the 126 MB L2; no flush needed",
+        "chunk_samples": 4096,
+    }
+    if nblocks is not None:
+        cfg["blocks_per_gpu"] = nblocks
+    return cfg
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--files", type=int, default=10000, help="files per GPU")
+    ap.add_argument("--seconds", type=float, default=10.0)
+    ap.add_argument("--gen-budget-s", type=float, default=60.0, help="time budget for encoding unique files")
+    ap.add_argument("--cpu-baseline-s", type=float, default=15.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        log("note: W < 3 requested; the timing rules want >= 3 warm-up steps")
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from wavpackdecoder_b200 import _native as N
+    from wavpackdecoder_b200.batch import BatchDecoder, Corpus
+
+    lib = N.load()
+    if lib.wvb_device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device; libwvb has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    threads = max(1, host_cores() // max(1, world))
+    t0 = time.perf_counter()
+    corpus = build_corpus(args.files, args.seconds, 0x5EED0000 + rank * args.files, threads, args.gen_budget_s, pin=True)
+    log("corpus: %d files (%d unique) %.2f GB compressed, generated in %.1f s (+%.1f s total) on %d threads" % (
+        args.files, corpus["unique"], corpus["compressed_bytes"] / 1e9, corpus["gen_s"], time.perf_counter() - t0, threads))
+
+    slab = corpus["slab"]
+    t0 = time.perf_counter()
+    cp = Corpus(slab, corpus["offsets"], corpus["sizes"], out_format=N.OUT_PCM, threads=threads)
+    index_s = time.perf_counter() - t0
+    total_samples = cp.total_samples
+    pcm_bytes = cp.out_bytes
+    log("index: %d blocks, %d samples, %.2f GB PCM, %.3f s" % (cp.nblocks, total_samples, pcm_bytes / 1e9, index_s))
+    assert all(cp.infos[i].status == 0 for i in range(cp.nfiles))
+
+    dec = BatchDecoder(local_rank)
+    dev = torch.device("cuda", local_rank)
+    d_in = torch.empty(slab.size, dtype=torch.uint8, device=dev)
+    d_in.copy_(corpus["slab_t"][:slab.size], non_blocking=False)
+    d_out = torch.empty(pcm_bytes + 64, dtype=torch.uint8, device=dev)
+    d_res = torch.empty(max(cp.nblocks, 1) * 16, dtype=torch.uint8, device=dev)
+    dec.prepare(cp.descs, cp.nblocks, N.OUT_PCM)
+    FL = N.IN_DEVICE | N.OUT_DEVICE | N.RESULTS_DEVICE
+
+    def step_resident():
+        dec.decode(d_in.data_ptr(), slab.size, None, cp.nblocks, d_out.data_ptr(), pcm_bytes, N.OUT_PCM, FL, d_res.data_ptr())
+
+    for _ in range(max(args.warmup, 1)):
+        step_resident()
+    # validation (untimed): no block may report a CRC error; three files are compared with the oracle byte for byte
+    res_host = d_res.cpu().numpy().view(np.uint32).reshape(-1, 4)
+    crc_errors = int((res_host[:cp.nblocks, 1] & 1).sum())
+    flagged = int((res_host[:cp.nblocks, 1] != 0).sum())
+    import _harness as H
+    validated = crc_errors == 0 and flagged == 0
+    for i in sorted({0, cp.nfiles // 2, cp.nfiles - 1}):
+        o = int(cp.file_out_offset[i])
+        nb = int(cp.infos[i].indexed_samples) * 4
+        got = d_out[o:o + nb].cpu().numpy()
+        data = slab[int(corpus["offsets"][i]):int(corpus["offsets"][i]) + int(corpus["sizes"][i])].tobytes()
+        ref, errs, status, info = H.oracle_decode(data)
+        validated = validated and status == 0 and errs == 0 and np.array_equal(got, H.format_samples(ref, 2))
+    log("validation vs oracle: %s (crc_errors=%d flagged=%d)" % (validated, crc_errors, flagged))
+
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    kernel_ms, launches = [], 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_resident()
+        tm = dec.timing()
+        kernel_ms.append(tm["kernel_ms"])
+        launches += tm["launches"]
+    torch.cuda.synchronize()
+    elapsed = time.perf_counter() - t0
+    clk = clocks.stop()
+    t = torch.tensor([elapsed], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_max = float(t.item())
+    value = total_samples * world * args.steps / elapsed_max
+
+    # ---- e2e: host buffers through the public C-ABI call, index pass + H2D + kernels + D2H every step ----
+    e2e = None
+    if not args.no_e2e:
+        out_t = torch.empty(pcm_bytes + 64, dtype=torch.uint8, pin_memory=True)
+        out_np = out_t.numpy()
+        results = (N.BlockResult * max(cp.nblocks, 1))()
+
+        def step_e2e():
+            c2 = Corpus(slab, corpus["offsets"], corpus["sizes"], out_format=N.OUT_PCM, threads=threads)
+            dec.decode(slab.ctypes.data, slab.size, c2.descs, c2.nblocks, out_np.ctypes.data, pcm_bytes, N.OUT_PCM, 0, results)
+            return c2
+
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            c2 = step_e2e()
+        torch.cuda.synchronize()
+        e_elapsed = time.perf_counter() - t0
+        t = torch.tensor([e_elapsed], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ok = all((results[i].rflags == 0) for i in range(0, cp.nblocks, max(1, cp.nblocks // 1000)))
+        e2e = {"value": total_samples * world * args.steps / float(t.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(slab.size + cp.nblocks * (144 + 4)), "d2h_bytes_per_step": int(pcm_bytes + cp.nblocks * 16),
+               "includes": "host block-index pass + H2D + kernels + D2H", "validated": bool(e2e_ok)}
+
+    # ---- roofline of the dominant kernel ----
+    peak, peak_kind = measured_peak()
+    k_ms = float(np.mean(kernel_ms))
+    algo_bytes = corpus["compressed_bytes"] + pcm_bytes
+    achieved = algo_bytes / (k_ms * 1e-3) / 1e9
+    traffic = ncu_traffic()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic.get("dram_bytes_per_launch") if traffic else None, "peak_kind": peak_kind,
+                "kernel": "k_decode_pcm<stereo,lossless>", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": int(algo_bytes),
+                "bytes_per_sample": algo_bytes / total_samples}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        n = size_cpu_sample(corpus, cores, args.cpu_baseline_s)
+        s, dt = cpu_decode_sample(corpus, n, cores)
+        cpu_baseline = {"value": s / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "%d of the %d files, one file per thread, decode + WavpackFormatSamples, %.1f s" % (n, args.files, dt)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * elapsed_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic (in-repo encoder, %d unique files per GPU, validated vs oracle: %s)" % (corpus["unique"], validated),
+            "config": workload_config(args, corpus, cp.nblocks), "clocks": clk, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "pcm_gb_per_s": pcm_bytes * world * args.steps / elapsed_max / 1e9, "validated": bool(validated),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

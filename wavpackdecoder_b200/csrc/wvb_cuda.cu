@@ -49,10 +49,10 @@ k_decode_pcm(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ 
 {
     extern __shared__ int smem[];
     const uint32_t i = blockIdx.x * CTA_THREADS + threadIdx.x;
-    if (i >= count) return;
-    const uint32_t bi = order[i];
+    const bool valid = i < count; // lanes past the end keep running (with no work): the decode loop is warp-synchronous
+    const uint32_t bi = order[valid ? i : count - 1];
     SharedColumn SM{smem + threadIdx.x};
-    wvb::decode_block_pcm<STEREO, HYB, GENFIX>(SM, in, descs[bi], out, out_format, &results[bi]);
+    wvb::decode_block_pcm<STEREO, HYB, GENFIX>(SM, in, descs[bi], out, out_format, &results[bi], valid);
 }
 
 } // namespace

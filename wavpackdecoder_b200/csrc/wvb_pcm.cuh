@@ -26,6 +26,8 @@ static __device__ __forceinline__ uint32_t wvb_ld_u32(const uint8_t *p) { return
 static __device__ __forceinline__ uint8_t wvb_ld_u8(const uint8_t *p) { return __ldg(p); }
 static __device__ __forceinline__ int wvb_ffs(uint32_t x) { return __ffs((int)x); }
 static __device__ __forceinline__ int wvb_clz(uint32_t x) { return __clz((int)x); }
+#define WVB_SYNCWARP() __syncwarp()
+static __device__ __forceinline__ uint32_t wvb_warp_max(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
 #else
 #include <string.h>
 #define WVB_DEV inline
@@ -35,6 +37,8 @@ static inline uint32_t wvb_ld_u32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 
 static inline uint8_t wvb_ld_u8(const uint8_t *p) { return *p; }
 static inline int wvb_ffs(uint32_t x) { return x ? __builtin_ctz(x) + 1 : 0; }
 static inline int wvb_clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
+#define WVB_SYNCWARP() ((void)0)
+static inline uint32_t wvb_warp_max(uint32_t v) { return v; }
 #endif
 
 namespace wvb {
@@ -182,7 +186,7 @@ WVB_DEV bool read_gamma(BitReader &br, uint32_t &value)
 }
 
 // read_code for ranges >= 2^30, where the reference's int/long mixing matters (WordsUtils.cs:546-570, quirk C-3)
-WVB_DEV_NOINLINE uint32_t read_code_wide(BitReader &br, uint32_t low, uint32_t range)
+WVB_DEV uint32_t read_code_wide(BitReader &br, uint32_t low, uint32_t range)
 {
     const int bitcount = 32 - wvb_clz(range);
     const int64_t extras = (int64_t)(int32_t)(1u << (bitcount & 31)) - (int64_t)range - 1;
@@ -196,123 +200,131 @@ WVB_DEV_NOINLINE uint32_t read_code_wide(BitReader &br, uint32_t low, uint32_t r
 }
 
 // One word of get_words for channel CH.  Returns false when the reference would `break` (EOF / error).
+// Written single-exit (no early returns, no goto): 32 lanes run this in lock step on different streams and must
+// reconverge at the end of every word, which the compiler only guarantees for structured control flow.
 template <bool HYB, bool STEREO, int CH> WVB_DEV bool decode_word(BitReader &br, Words<HYB> &w, uint32_t flags, int &out)
 {
     int *med = w.m[CH];
-    if (((w.m[0][0] | w.m[1][0]) & ~1) == 0 && w.hold == 0) { // WordsUtils.cs:304-352
+    bool ok = true, done = false;
+    out = 0;
+    if (((w.m[0][0] | w.m[1][0]) & ~1) == 0 && w.hold == 0) { // zero-run regime, WordsUtils.cs:304-352
         if (w.zeros_acc > 0) {
-            if (--w.zeros_acc > 0) {
-                if constexpr (HYB) w.slow[CH] -= (w.slow[CH] + 128) >> 8;
-                out = 0;
-                return true;
-            }
+            if (--w.zeros_acc > 0) done = true;
         } else {
-            uint32_t z;
-            if (!read_gamma(br, z)) return false;
-            w.zeros_acc = z;
-            if (z > 0) {
-                if constexpr (HYB) w.slow[CH] -= (w.slow[CH] + 128) >> 8;
-                w.m[0][0] = w.m[0][1] = w.m[0][2] = 0;
-                w.m[1][0] = w.m[1][1] = w.m[1][2] = 0;
-                out = 0;
-                return true;
-            }
-        }
-    }
-
-    br.refill(); // >= 33 bits
-    int ones;
-    if (w.hold == 2) { // WordsUtils.cs:354-358
-        w.hold = 0;
-        ones = 0;
-    } else { // WordsUtils.cs:361-428
-        int t = wvb_ffs(~br.peek()) - 1;
-        if ((unsigned)t >= 16u) {
-            br.consume(16);
-            if (br.getbit()) return false; // 17 ones: end of stream
-            uint32_t v;
-            if (!read_gamma(br, v)) return false;
-            t = (int)v + 16;
-            br.refill();
-        } else
-            br.consume(t + 1);
-        const int h1 = w.hold == 1;
-        w.hold = (t & 1) ? 1 : 2;
-        ones = (t >> 1) + h1;
-    }
-
-    if constexpr (HYB && CH == 0) update_error_limit<STEREO>(w, flags); // WordsUtils.cs:430-431
-
-    uint32_t low, high; // WordsUtils.cs:433-475
-    {
-        const int g0 = (med[0] >> 4) + 1;
-        if (ones == 0) {
-            low = 0;
-            high = (uint32_t)g0 - 1;
-            med[0] -= ((med[0] + 126) >> 7) * 2;
-        } else {
-            low = (uint32_t)g0;
-            med[0] += ((med[0] + 128) >> 7) * 5;
-            const int g1 = (med[1] >> 4) + 1;
-            if (ones == 1) {
-                high = low + (uint32_t)g1 - 1;
-                med[1] -= ((med[1] + 62) >> 6) * 2;
-            } else {
-                low += (uint32_t)g1;
-                med[1] += ((med[1] + 64) >> 6) * 5;
-                const int g2 = (med[2] >> 4) + 1;
-                if (ones == 2) {
-                    high = low + (uint32_t)g2 - 1;
-                    med[2] -= ((med[2] + 30) >> 5) * 2;
-                } else {
-                    low += (uint32_t)((ones - 2) * g2);
-                    high = low + (uint32_t)g2 - 1;
-                    med[2] += ((med[2] + 32) >> 5) * 5;
+            uint32_t z = 0;
+            ok = read_gamma(br, z);
+            if (ok) {
+                w.zeros_acc = z;
+                if (z > 0) {
+                    w.m[0][0] = w.m[0][1] = w.m[0][2] = 0;
+                    w.m[1][0] = w.m[1][1] = w.m[1][2] = 0;
+                    done = true;
                 }
             }
         }
+        if (done) {
+            if constexpr (HYB) w.slow[CH] -= (w.slow[CH] + 128) >> 8;
+        }
     }
 
-    uint32_t mid;
-    bool lossless_code = true;
-    if constexpr (HYB) lossless_code = w.errlim[CH] == 0;
-    if (lossless_code) { // read_code, WordsUtils.cs:546-570
-        const uint32_t range = high - low;
-        uint32_t code = 0;
-        if (range) {
-            const int bitcount = 32 - wvb_clz(range);
-            if (bitcount >= 31) {
-                mid = read_code_wide(br, low, range);
-                goto have_mid;
+    if (ok && !done) {
+        br.refill(); // >= 33 bits
+        int ones = 0;
+        if (w.hold == 2) { // WordsUtils.cs:354-358
+            w.hold = 0;
+        } else { // WordsUtils.cs:361-428
+            int t = wvb_ffs(~br.peek()) - 1;
+            if ((unsigned)t >= 16u) {
+                br.consume(16);
+                if (br.getbit()) ok = false; // 17 ones: end of stream
+                else {
+                    uint32_t v = 0;
+                    ok = read_gamma(br, v);
+                    t = (int)v + 16;
+                    br.refill();
+                }
+            } else
+                br.consume(t + 1);
+            const int h1 = w.hold == 1;
+            w.hold = (t & 1) ? 1 : 2;
+            ones = (t >> 1) + h1;
+        }
+
+        if (ok) {
+            if constexpr (HYB && CH == 0) update_error_limit<STEREO>(w, flags); // WordsUtils.cs:430-431
+
+            uint32_t low, high; // WordsUtils.cs:433-475
+            {
+                const int g0 = (med[0] >> 4) + 1;
+                if (ones == 0) {
+                    low = 0;
+                    high = (uint32_t)g0 - 1;
+                    med[0] -= ((med[0] + 126) >> 7) * 2;
+                } else {
+                    low = (uint32_t)g0;
+                    med[0] += ((med[0] + 128) >> 7) * 5;
+                    const int g1 = (med[1] >> 4) + 1;
+                    if (ones == 1) {
+                        high = low + (uint32_t)g1 - 1;
+                        med[1] -= ((med[1] + 62) >> 6) * 2;
+                    } else {
+                        low += (uint32_t)g1;
+                        med[1] += ((med[1] + 64) >> 6) * 5;
+                        const int g2 = (med[2] >> 4) + 1;
+                        if (ones == 2) {
+                            high = low + (uint32_t)g2 - 1;
+                            med[2] -= ((med[2] + 30) >> 5) * 2;
+                        } else {
+                            low += (uint32_t)((ones - 2) * g2);
+                            high = low + (uint32_t)g2 - 1;
+                            med[2] += ((med[2] + 32) >> 5) * 5;
+                        }
+                    }
+                }
             }
-            const uint32_t extras = (1u << bitcount) - range - 1u;
+
+            uint32_t mid;
+            bool lossless_code = true;
+            if constexpr (HYB) lossless_code = w.errlim[CH] == 0;
+            if (lossless_code) { // read_code, WordsUtils.cs:546-570
+                const uint32_t range = high - low;
+                mid = low;
+                if (range) {
+                    const int bitcount = 32 - wvb_clz(range);
+                    if (bitcount >= 31)
+                        mid = read_code_wide(br, low, range);
+                    else {
+                        const uint32_t extras = (1u << bitcount) - range - 1u;
+                        br.refill();
+                        uint32_t code = br.peek() & ((1u << (bitcount - 1)) - 1u);
+                        br.consume(bitcount - 1);
+                        if (code >= extras) {
+                            code = (code << 1) - extras + (br.peek() & 1u);
+                            br.consume(1);
+                        }
+                        mid = low + code;
+                    }
+                }
+            } else { // WordsUtils.cs:477-492
+                uint32_t lim = 0;
+                if constexpr (HYB) lim = (uint32_t)w.errlim[CH];
+                mid = (uint32_t)(((uint64_t)high + low + 1) >> 1);
+                while (high - low > lim) {
+                    if (br.getbit()) low = mid;
+                    else high = mid - 1;
+                    mid = (uint32_t)(((uint64_t)high + low + 1) >> 1);
+                }
+            }
             br.refill();
-            code = br.peek() & ((1u << (bitcount - 1)) - 1u);
-            br.consume(bitcount - 1);
-            if (code >= extras) {
-                code = (code << 1) - extras + (br.peek() & 1u);
-                br.consume(1);
+            out = (br.peek() & 1u) ? (int)~mid : (int)mid; // WordsUtils.cs:494-497
+            br.consume(1);
+            if constexpr (HYB) {
+                if (flags & F_HYB_BITRATE) // WordsUtils.cs:501-502
+                    w.slow[CH] = w.slow[CH] - ((w.slow[CH] + 128) >> 8) + mylog2(mid);
             }
         }
-        mid = low + code;
-    } else if constexpr (HYB) { // WordsUtils.cs:477-492
-        const uint32_t lim = (uint32_t)w.errlim[CH];
-        mid = (uint32_t)(((uint64_t)high + low + 1) >> 1);
-        while (high - low > lim) {
-            if (br.getbit()) low = mid;
-            else high = mid - 1;
-            mid = (uint32_t)(((uint64_t)high + low + 1) >> 1);
-        }
     }
-have_mid:
-    br.refill();
-    out = (br.peek() & 1u) ? (int)~mid : (int)mid; // WordsUtils.cs:494-497
-    br.consume(1);
-    if constexpr (HYB) {
-        if (flags & F_HYB_BITRATE) // WordsUtils.cs:501-502
-            w.slow[CH] = w.slow[CH] - ((w.slow[CH] + 128) >> 8) + mylog2(mid);
-    }
-    return true;
+    return ok;
 }
 
 // ---- decorrelation ---------------------------------------------------------------------------
@@ -537,11 +549,15 @@ WVB_DEV void store_unit(uint8_t *q, int v, int unit, int add128)
 // ---- the per-thread block decoder ------------------------------------------------------------
 // STEREO: two coded channels (neither MONO_FLAG nor FALSE_STEREO).  HYB: HYBRID_FLAG.  GENFIX: float / int32 / hybrid fixup.
 template <bool STEREO, bool HYB, bool GENFIX, class SMEM>
-WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc &D, uint8_t *out, int out_format, wvb_block_result *res)
+WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc &D, uint8_t *out, int out_format, wvb_block_result *res,
+                              bool valid = true)
 {
     const uint8_t *blk = in + D.in_offset;
     const uint32_t flags = D.flags;
-    const uint32_t n = D.block_samples;
+    // lanes without a block (tail of the grid) and MUTE_ALL blocks stay in the warp with n == 0: every lane must reach
+    // the warp-wide operations of the sample loop
+    const bool mute_all = (D.bflags & WVB_BF_MUTE_ALL) != 0;
+    const uint32_t n = (valid && !mute_all) ? D.block_samples : 0;
     const int unit = out_format == WVB_OUT_INT32 ? 4 : (int)D.out_bps;
     const int add128 = (out_format == WVB_OUT_PCM && unit == 1) ? 128 : 0;
     const uint32_t frame_bytes = (uint32_t)unit * D.out_stride;
@@ -549,17 +565,17 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
     uint8_t *op = out + D.out_offset + (uint32_t)unit * D.out_ch_offset;
     uint32_t rflags = 0;
 
-    if (D.gap_before) { // zero fill before the block (WavPackUtils.cs:227-251)
+    if (valid && D.gap_before) { // zero fill before the block (WavPackUtils.cs:227-251)
         uint8_t *g = out + D.out_offset - (uint64_t)D.gap_before * frame_bytes;
         for (uint32_t i = 0; i < D.gap_before; ++i, g += frame_bytes)
             for (int c = 0; c < D.out_stride; ++c) store_unit(g + c * unit, 0, unit, add128);
     }
-    if (D.bflags & WVB_BF_MUTE_ALL) {
-        for (uint32_t i = 0; i < n; ++i, op += frame_bytes)
-            for (int c = 0; c < out_ch; ++c) store_unit(op + c * unit, 0, unit, add128);
+    if (valid && mute_all) {
+        uint8_t *q = op;
+        for (uint32_t i = 0; i < D.block_samples; ++i, q += frame_bytes)
+            for (int c = 0; c < out_ch; ++c) store_unit(q + c * unit, 0, unit, add128);
         res->crc = -1; res->crc_x = -1; res->mute_from = 0;
         res->rflags = WVB_RF_MUTED | WVB_RF_CRC_ERROR | WVB_RF_INEXACT;
-        return;
     }
     if (D.bflags & WVB_BF_STALE_STATE) rflags |= WVB_RF_INEXACT;
 
@@ -714,47 +730,58 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
     uint32_t trunc8 = (STEREO && piece_end - piece_start >= 16) ? piece_start + 8 : 0xffffffffu;
 
     int crc = -1;
-    uint32_t t = 0;
     bool fault = false, eof_fault = false;
-    for (; t < n; ++t) {
-        if (t == piece_end) {
-            truncate_weights<STEREO>(SM, nterms);
-            piece_start = t;
-            const uint32_t rest = n - t;
-            piece_end = t + (chunk < rest ? chunk : rest);
-            trunc8 = (STEREO && piece_end - piece_start >= 16) ? piece_start + 8 : 0xffffffffu;
-        } else if (t == trunc8)
-            truncate_weights<STEREO>(SM, nterms);
-
-        int a, b = 0;
-        if (!decode_word<HYB, STEREO, 0>(br, w, flags, a)) { fault = eof_fault = true; break; }
-        if (STEREO && !decode_word<HYB, STEREO, 1>(br, w, flags, b)) { fault = eof_fault = true; break; }
-
-        decorr_frame<STEREO>(SM, nterms, t, a, b);
-
-        if (joint) { b -= (a >> 1); a += b; } // UnpackUtils.cs:615 (App. E-9)
-        {
+    // All 32 lanes of a warp iterate together (warp-max trip count) and re-join at the top of every sample:
+    // a lane left behind by a divergent branch must not be allowed to run the rest of its block alone.
+    const uint32_t nmax = wvb_warp_max(n);
+    for (uint32_t t = 0; t < nmax; ++t) {
+        WVB_SYNCWARP();
+        const bool act = t < n && !fault;
+        if (act) {
+            if (t == piece_end) {
+                truncate_weights<STEREO>(SM, nterms);
+                piece_start = t;
+                const uint32_t rest = n - t;
+                piece_end = t + (chunk < rest ? chunk : rest);
+                trunc8 = (STEREO && piece_end - piece_start >= 16) ? piece_start + 8 : 0xffffffffu;
+            } else if (t == trunc8)
+                truncate_weights<STEREO>(SM, nterms);
+        }
+        int a = 0, b = 0;
+        bool ok = act;
+        if (ok) ok = decode_word<HYB, STEREO, 0>(br, w, flags, a);
+        WVB_SYNCWARP();
+        if (STEREO) {
+            if (ok) ok = decode_word<HYB, STEREO, 1>(br, w, flags, b);
+            WVB_SYNCWARP();
+        }
+        if (act && !ok) eof_fault = true;
+        if (ok) {
+            decorr_frame<STEREO>(SM, nterms, t, a, b);
+            if (joint) { b -= (a >> 1); a += b; } // UnpackUtils.cs:615 (App. E-9)
             const int aa = a < 0 ? -a : a, ab = b < 0 ? -b : b;
-            if (aa > mute_limit || (STEREO && ab > mute_limit)) { fault = true; break; }
+            if (aa > mute_limit || (STEREO && ab > mute_limit)) ok = false;
         }
-        crc = crc * 3 + a;
-        if (STEREO) crc = crc * 3 + b;
-
-        if (fast16) {
-            *(uint32_t *)op = ((uint32_t)shl32(a, fx.shift) & 0xffffu) | ((uint32_t)shl32(b, fx.shift) << 16);
-        } else {
-            int va, vb = 0;
-            if (GENFIX) {
-                va = fixup_value(fx, a, wvx, crc_x);
-                if (STEREO) vb = fixup_value(fx, b, wvx, crc_x);
+        if (ok) {
+            crc = crc * 3 + a;
+            if (STEREO) crc = crc * 3 + b;
+            if (fast16) {
+                *(uint32_t *)op = ((uint32_t)shl32(a, fx.shift) & 0xffffu) | ((uint32_t)shl32(b, fx.shift) << 16);
             } else {
-                va = shl32(a, fx.shift);
-                if (STEREO) vb = shl32(b, fx.shift);
+                int va, vb = 0;
+                if (GENFIX) {
+                    va = fixup_value(fx, a, wvx, crc_x);
+                    if (STEREO) vb = fixup_value(fx, b, wvx, crc_x);
+                } else {
+                    va = shl32(a, fx.shift);
+                    if (STEREO) vb = shl32(b, fx.shift);
+                }
+                store_unit(op, va, unit, add128);
+                if (out_ch == 2) store_unit(op + unit, STEREO ? vb : va, unit, add128); // FALSE_STEREO duplicates (UnpackUtils.cs:668-680)
             }
-            store_unit(op, va, unit, add128);
-            if (out_ch == 2) store_unit(op + unit, STEREO ? vb : va, unit, add128); // FALSE_STEREO duplicates (UnpackUtils.cs:668-680)
+            op += frame_bytes;
         }
-        op += frame_bytes;
+        if (act && !ok) fault = true;
     }
 
     if (fault) { // mute from the start of the caller chunk that contains the fault (UnpackUtils.cs:649-664, App. E-10)
@@ -774,6 +801,7 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
     } else
         res->mute_from = n;
 
+    if (!valid || mute_all) return;
     // check_crc_error, UnpackUtils.cs:1414-1421
     if (crc != D.crc || eof_fault) rflags |= WVB_RF_CRC_ERROR; // after a short get_words the reference's crc runs over stale buffer contents
     if (GENFIX && !(flags & F_FLOAT) && (D.bflags & WVB_BF_WVX_PRESENT)) {
