@@ -106,7 +106,7 @@ pcm_kernel_t pcm_kernel(int variant)
 }
 
 // shared-memory size classes (words per thread); a launch uses the smallest class that fits its blocks
-const int kSmemClasses[] = {32, 64, 96, 128, 192, 256, 320, 448};
+const int kSmemClasses[] = {8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 128, 160, 192, 256, 320, 448};
 int smem_class(int words)
 {
     for (int c : kSmemClasses)

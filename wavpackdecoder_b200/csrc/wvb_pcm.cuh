@@ -85,10 +85,11 @@ WVB_DEV int restore_weight(int w8) // WordsUtils.cs:653-661, w8 already sign-ext
 // buffer with 0xFF on overrun, BitsUtils.cs:132-146).  A plain LSB-first window is bit-identical to
 // getbit/getbits.
 struct BitReader {
-    const uint8_t *next; // 4-byte aligned address of the next word
+    const uint8_t *next; // 4-byte aligned address of the next word to fetch
     const uint8_t *end;
-    uint64_t bb;
-    int bc;
+    uint64_t bb;  // bit window, LSB = next bit
+    int bc;       // valid bits in bb
+    uint32_t nw;  // word fetched one refill ahead: its load latency overlaps the decode of the bits before it
 
     WVB_DEV uint32_t load_word()
     {
@@ -107,12 +108,14 @@ struct BitReader {
         const uint32_t x = load_word();
         bb = x >> (8 * mis);
         bc = 32 - 8 * mis;
+        nw = load_word();
     }
-    WVB_DEV void refill()
+    WVB_DEV void refill() // afterwards bc >= 33
     {
         if (bc <= 32) {
-            bb |= (uint64_t)load_word() << bc;
+            bb |= (uint64_t)nw << bc;
             bc += 32;
+            nw = load_word();
         }
     }
     WVB_DEV void consume(int n) { bb >>= n; bc -= n; }
@@ -295,7 +298,7 @@ template <bool HYB, bool STEREO, int CH> WVB_DEV bool decode_word(BitReader &br,
                         mid = read_code_wide(br, low, range);
                     else {
                         const uint32_t extras = (1u << bitcount) - range - 1u;
-                        br.refill();
+                        if (br.bc <= bitcount) br.refill(); // need bitcount-1 code bits + 1 extra + 1 sign
                         uint32_t code = br.peek() & ((1u << (bitcount - 1)) - 1u);
                         br.consume(bitcount - 1);
                         if (code >= extras) {
@@ -315,7 +318,7 @@ template <bool HYB, bool STEREO, int CH> WVB_DEV bool decode_word(BitReader &br,
                     mid = (uint32_t)(((uint64_t)high + low + 1) >> 1);
                 }
             }
-            br.refill();
+            if (br.bc == 0) br.refill();
             out = (br.peek() & 1u) ? (int)~mid : (int)mid; // WordsUtils.cs:494-497
             br.consume(1);
             if constexpr (HYB) {
