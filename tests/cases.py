@@ -53,3 +53,73 @@ PCM_CASES = [
     ("unknown_len", 0, 4096, dict(unknown_length=1)),
     ("all_hist_same_terms", 0, 4096, dict(extras=128, terms=[2, 2, 2])),
 ]
+
+from _harness import KIND_DSD  # noqa: E402
+
+DSD_CASES = [
+    ("dsd0_mono", 0, 4096, dict(kind=KIND_DSD, dsd_mode=0, channels=1, seconds=0.1, block_samples=8192)),
+    ("dsd0_stereo", 0, 4096, dict(kind=KIND_DSD, dsd_mode=0, seconds=0.1, block_samples=8192)),
+    ("dsd1_mono", 0, 4096, dict(kind=KIND_DSD, dsd_mode=1, channels=1, seconds=0.1, block_samples=8192)),
+    ("dsd1_stereo", 0, 4096, dict(kind=KIND_DSD, dsd_mode=1, seconds=0.1, block_samples=8192)),
+    ("dsd1_raw_probs", 0, 4096, dict(kind=KIND_DSD, dsd_mode=1, dsd_raw_probs=1, dsd_history_bits=2, seconds=0.1, block_samples=8192)),
+    ("dsd1_h0_chunk1000", 0, 1000, dict(kind=KIND_DSD, dsd_mode=1, dsd_history_bits=0, seconds=0.1, block_samples=5000)),
+    ("dsd1_h5", 0, 4096, dict(kind=KIND_DSD, dsd_mode=1, dsd_history_bits=5, seconds=0.15, block_samples=22050)),
+    ("dsd3_mono", 0, 4096, dict(kind=KIND_DSD, dsd_mode=3, channels=1, seconds=0.1, block_samples=8192)),
+    ("dsd3_stereo", 0, 4096, dict(kind=KIND_DSD, dsd_mode=3, seconds=0.1, block_samples=8192)),
+    ("dsd3_rate200", 0, 4096, dict(kind=KIND_DSD, dsd_mode=3, dsd_rate_i=200, seconds=0.1, block_samples=5000)),
+    ("dsd3_extras", 0, 4096, dict(kind=KIND_DSD, dsd_mode=3, seconds=0.1, block_samples=8192, extras=2 | 4 | 8 | 16)),
+]
+
+
+def _blocks(data):
+    import struct
+    off, out = 0, []
+    while off + 32 <= len(data):
+        cks = struct.unpack_from("<I", data, off + 4)[0]
+        out.append((off, cks + 8))
+        off += cks + 8
+    return out
+
+
+def corrupt_cases():
+    """(name, bytes, open_flags, chunk): damaged streams, the domain's "erasures".  Expected behaviour is whatever the
+    oracle does: mute from the start of the caller chunk, CRC error counts, truncated output, gap zero fill, 0x55 DSD mute."""
+    from _harness import make_file
+    out = []
+    cfg, src, data = make_file(seconds=2.0)
+    bl = _blocks(data)
+
+    def flip(d, at, mask=0x40):
+        d = bytearray(d)
+        d[at] ^= mask
+        return bytes(d)
+
+    mid1 = bl[1][0] + bl[1][1] // 2
+    out.append(("flip_bitstream", flip(data, mid1), 0, 4096))
+    out.append(("flip_bitstream_chunk1000", flip(data, mid1), 0, 1000))
+    out.append(("flip_header_crc", flip(data, bl[2][0] + 28, 1), 0, 4096))
+    out.append(("truncated_midblock", data[:bl[2][0] + bl[2][1] // 2], 0, 4096))
+    out.append(("truncated_in_header", data[:bl[2][0] + 20], 0, 4096))
+    out.append(("dropped_block_gap", data[:bl[1][0]] + data[bl[2][0]:], 0, 4096))
+    out.append(("garbage_between_blocks", data[:bl[1][0]] + b"\x00wvpk garbage 12345" * 3 + data[bl[1][0]:], 0, 4096))
+    out.append(("flip_tail_in_silence", flip(data, bl[1][0] + bl[1][1] - 3, 0xff), 0, 4096))
+    d = bytearray(data)
+    for k in range(200):
+        d[bl[1][0] + 300 + k] = 0xff
+    out.append(("ones_burst", bytes(d), 0, 4096))
+    cfg, src, datam = make_file(seconds=2.0, channels=1)
+    blm = _blocks(datam)
+    out.append(("mono_flip", flip(datam, blm[1][0] + blm[1][1] // 2, 0x10), 0, 4096))
+    out.append(("mono_flip_chunk777", flip(datam, blm[1][0] + blm[1][1] // 2, 0x10), 0, 777))
+    cfg, src, datah = make_file(seconds=2.0, kind=1)
+    blh = _blocks(datah)
+    out.append(("hybrid_flip", flip(datah, blh[1][0] + blh[1][1] // 2, 0x10), 0, 4096))
+    cfg, src, datai = make_file(seconds=2.0, bits=32, int32_sent_bits=8)
+    bli = _blocks(datai)
+    out.append(("int32_flip_main", flip(datai, bli[1][0] + 2000, 0x10), 0, 4096))
+    for m in (0, 1, 3):
+        cfg, src, dd = make_file(kind=KIND_DSD, dsd_mode=m, seconds=0.3, block_samples=20000)
+        bd = _blocks(dd)
+        out.append(("dsd%d_flip" % m, flip(dd, bd[1][0] + bd[1][1] // 2, 0x04), 0, 4096))
+        out.append(("dsd%d_flip_chunk3000" % m, flip(dd, bd[1][0] + bd[1][1] // 2, 0x04), 0, 3000))
+    return out

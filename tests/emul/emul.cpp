@@ -5,6 +5,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../wavpackdecoder_b200/csrc/wvb_dsd_core.cuh"
 #include "../../wavpackdecoder_b200/csrc/wvb_pcm.cuh"
 #include "../../wavpackdecoder_b200/csrc/wvb_plan.h"
 
@@ -30,9 +31,63 @@ extern "C" int emul_decode(const uint8_t *in, const wvb_block_desc *descs, size_
         case wvb::V_STEREO | wvb::V_GENFIX: wvb::decode_block_pcm<true, false, true>(sm, in, D, out, out_format, &r); break;
         case wvb::V_MONO | wvb::V_GENFIX | wvb::V_HYBRID: wvb::decode_block_pcm<false, true, true>(sm, in, D, out, out_format, &r); break;
         case wvb::V_STEREO | wvb::V_GENFIX | wvb::V_HYBRID: wvb::decode_block_pcm<true, true, true>(sm, in, D, out, out_format, &r); break;
+        case wvb::V_DSD: {
+            const int mode = wvb::dsd_key_mode(D.smem_words);
+            if (mode == 0)
+                wvb::dsd_decode_raw(in, D, out, out_format, &r);
+            else if (mode == 3) {
+                int pt0[256];
+                wvb::dsd_init_ptable_host(pt0, wvb::dsd_key_rate(D.smem_words), 20);
+                HostSM pt;
+                pt.w.assign(256, 0);
+                wvb::dsd_decode_high(pt, pt0, in, D, out, out_format, &r, true);
+            } else if (mode == 1) {
+                std::vector<uint8_t> prob(32 * 256);
+                std::vector<uint16_t> summed(32 * 256);
+                wvb::DsdFastTables T{prob.data(), summed.data()};
+                const uint8_t *p = in + D.in_offset + D.sub_off[WVB_SUB_DSD];
+                const uint32_t len = D.sub_len[WVB_SUB_DSD];
+                int bins = 1;
+                uint32_t at = wvb::dsd_fast_build(T, p, len, 0, 1, bins);
+                if (!at) { r.rflags = WVB_RF_BAD_BLOCK; break; }
+                wvb::dsd_fast_sums(T, bins, 0, 1, [](uint32_t) { return 0u; });
+                wvb::DsdOut o;
+                wvb::dsd_out_init(o, D, out, out_format);
+                const bool mono = o.coded_ch == 1;
+                const uint32_t total = D.block_samples * (uint32_t)o.coded_ch;
+                int crc = -1;
+                bool failed = false;
+                uint32_t fail_at = total;
+                wvb::dsd_fast_decode(T, bins, p, len, at, mono, total,
+                    [](const uint16_t *row, uint32_t index) { int c = 0; for (int k = 0; k < 256; k++) c += row[k] <= index; return c; },
+                    [&](uint32_t j, int code) { o.put(j, code); }, crc, failed, fail_at);
+                wvb::dsd_finish(D, &r, crc, failed, mono ? fail_at : fail_at >> 1, 0);
+            } else
+                r.rflags = WVB_RF_BAD_BLOCK;
+            break;
+        }
         default: r.rflags = WVB_RF_BAD_BLOCK; break;
         }
         if (results) results[i] = r;
+    }
+    // DSD mute pass (k_dsd_mute_fix): 0x55 fill of muted pieces
+    for (size_t i = 0; i < n; i++) {
+        const wvb_block_desc &D = descs[i];
+        if (wvb::variant_of(D) != wvb::V_DSD || !results || !(results[i].rflags & WVB_RF_MUTED)) continue;
+        const int unit = out_format == WVB_OUT_INT32 ? 4 : 1, add = out_format == WVB_OUT_PCM ? 128 : 0;
+        const uint32_t fb = (uint32_t)unit * D.out_stride, nn = D.block_samples, chunk = D.chunk_samples ? D.chunk_samples : 0xffffffffu;
+        uint32_t first_len = D.chunk_first < nn ? D.chunk_first : nn;
+        if (first_len == 0) first_len = chunk < nn ? chunk : nn;
+        uint32_t ps = results[i].mute_from;
+        while (ps < nn) {
+            const uint32_t pe = ps < first_len ? first_len : (ps + chunk < nn ? ps + chunk : nn);
+            int64_t start = ps;
+            if (ps == 0 && D.chunk_first != 0 && D.chunk_first < chunk) start = -(int64_t)(chunk - D.chunk_first);
+            uint8_t *q = out + D.out_offset + start * (int64_t)fb;
+            for (uint32_t k = 0; k < pe - ps; ++k, q += fb)
+                for (int c = 0; c < D.out_stride; ++c) wvb::store_unit(q + c * unit, 0x55, unit, add);
+            ps = pe;
+        }
     }
     return 0;
 }

@@ -6,10 +6,10 @@ import numpy as np
 import pytest
 
 from _harness import emul_decode_file, format_samples, make_file, oracle_decode
-from cases import PCM_CASES
+from cases import DSD_CASES, PCM_CASES, corrupt_cases
 
 
-@pytest.mark.parametrize("name,flags,chunk,kw", PCM_CASES, ids=[c[0] for c in PCM_CASES])
+@pytest.mark.parametrize("name,flags,chunk,kw", PCM_CASES + DSD_CASES, ids=[c[0] for c in PCM_CASES + DSD_CASES])
 def test_device_code_on_host_matches_oracle(name, flags, chunk, kw):
     kw = dict(kw)
     if "nsamples" not in kw:
@@ -27,6 +27,18 @@ def test_device_code_on_host_matches_oracle(name, flags, chunk, kw):
     assert finfo.total_samples == info["num_samples"]
     assert finfo.num_channels == info["num_channels"]
     assert finfo.bytes_per_sample == info["bytes_per_sample"]
-    assert finfo.bits_per_sample == info["bits_per_sample"]
+    assert (finfo.bits_per_sample // 8 if finfo.dsd_multiplier else finfo.bits_per_sample) == info["bits_per_sample"]  # WavPackUtils.cs:412
     assert bool(finfo.five) == info["is_five"]
     assert finfo.version == info["version"]
+
+
+CORRUPT = corrupt_cases()
+
+
+@pytest.mark.parametrize("name,data,flags,chunk", CORRUPT, ids=[c[0] for c in CORRUPT])
+def test_damaged_streams_follow_the_oracle(name, data, flags, chunk):
+    ref, errs, status, info = oracle_decode(data, flags, chunk)
+    assert status == 0
+    out, finfo, res, descs = emul_decode_file(data, flags, chunk, 0)
+    assert out.size == ref.size and np.array_equal(out, ref)
+    assert sum(1 for r in res if r.rflags & 1) == errs

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from _harness import format_samples, make_file, oracle_decode
-from cases import PCM_CASES
+from cases import DSD_CASES, PCM_CASES, corrupt_cases
 
 pytestmark = pytest.mark.gpu
 
@@ -27,7 +27,7 @@ def _decode(files, flags, chunk, fmt):
     return decode_files(files, open_flags=flags, chunk_samples=chunk, out_format=fmt)
 
 
-@pytest.mark.parametrize("name,flags,chunk,kw", PCM_CASES, ids=[c[0] for c in PCM_CASES])
+@pytest.mark.parametrize("name,flags,chunk,kw", PCM_CASES + DSD_CASES, ids=[c[0] for c in PCM_CASES + DSD_CASES])
 def test_synthetic_case_matches_oracle(gpu, name, flags, chunk, kw):
     cfg, src, data = make_file(**kw)
     ref, errs, status, info = oracle_decode(data, flags, chunk)
@@ -72,3 +72,26 @@ def test_mixed_batch_one_launch_set(gpu):
     for (ref, errs, info), (pcm, gerrs, ginfo, results) in zip(refs, res):
         assert gerrs == errs
         assert np.array_equal(pcm, format_samples(ref, info["bytes_per_sample"]))
+
+
+def test_damaged_streams_follow_the_oracle(gpu):
+    """Corrupt / truncated / gapped streams in one batch: muting, CRC error counts and output length as the oracle."""
+    cases = corrupt_cases()
+    for chunk in sorted({c[3] for c in cases}):
+        group = [c for c in cases if c[3] == chunk]
+        res = _decode([c[1] for c in group], 0, chunk, gpu.OUT_INT32)
+        for (name, data, flags, _), (out, gerrs, info, results) in zip(group, res):
+            ref, errs, status, rinfo = oracle_decode(data, flags, chunk)
+            assert status == 0, name
+            assert out.size == ref.size and np.array_equal(out, ref), name
+            assert gerrs == errs, name
+
+
+def test_dsd_raw_output_format(gpu):
+    """WVB_OUT_DSD_RAW == WavpackFormatSamples(..., dsd: true): bytes copied without the +128 of the 8-bit PCM path."""
+    cfg, src, data = make_file(kind=3, dsd_mode=3, seconds=0.1, block_samples=8192)
+    ref, errs, status, info = oracle_decode(data)
+    (raw, _, _, _), = _decode([data], 0, 4096, gpu.OUT_DSD_RAW)
+    assert np.array_equal(raw, format_samples(ref, 1, dsd=True))
+    (pcm, _, _, _), = _decode([data], 0, 4096, gpu.OUT_PCM)
+    assert np.array_equal(pcm, format_samples(ref, 1, dsd=False))

@@ -303,9 +303,9 @@ int wvb_batch_decode(wvb_batch *b, const uint8_t *in, size_t in_bytes, const wvb
     const int fmt = out_format;
     for (const Launch &L : b->plan) {
         if (L.variant == wvb::V_DSD) {
-            if ((rc = wvb::launch_dsd(L.cls, din, b->d_descs, b->d_order + L.first, L.count, dout, fmt, dres, s, b->smem_optin)) != WVB_OK)
-                return set_error(rc, std::string("DSD launch: ") + cudaGetErrorString(cudaGetLastError()));
-            b->launches++;
+            if ((rc = wvb::launch_dsd(L.cls, din, b->d_descs, b->d_order + L.first, L.count, dout, fmt, dres, s, b->smem_optin, b->device,
+                                      &b->launches)) != WVB_OK)
+                return set_error(rc, std::string("DSD launch failed (unsupported dsd mode or CUDA error): ") + cudaGetErrorString(cudaGetLastError()));
             continue;
         }
         pcm_kernel_t k = pcm_kernel(L.variant);
@@ -318,6 +318,9 @@ int wvb_batch_decode(wvb_batch *b, const uint8_t *in, size_t in_bytes, const wvb
         CUDA_TRY(cudaGetLastError());
         b->launches++;
     }
+    for (const Launch &L : b->plan) // 0x55 fill of muted DSD pieces, after every decode thread has finished
+        if (L.variant == wvb::V_DSD && (rc = wvb::launch_dsd_mute_fix(b->d_descs, b->d_order + L.first, L.count, dout, fmt, dres, s, &b->launches)) != WVB_OK)
+            return set_error(rc, "DSD mute pass failed");
     CUDA_TRY(cudaEventRecord(b->ev[2], s));
 
     if (!(mem_flags & WVB_OUT_DEVICE)) CUDA_TRY(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, s));

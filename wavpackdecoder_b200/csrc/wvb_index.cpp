@@ -347,6 +347,8 @@ bool unpack_init(Ctx &c)
                 return fail_id(id);
             c.dsd_ready = true;
             B.sub_off[WVB_SUB_DSD] = rel; B.sub_len[WVB_SUB_DSD] = (uint32_t)n;
+            // planner key (see wvb_dsd_core.cuh): mode | history_bits << 4 | rate_i << 8
+            B.smem_words = (uint16_t)((mode & 15) | (mode == 1 ? (p[2] & 15) << 4 : 0) | (mode == 3 ? p[2] << 8 : 0));
             if (n != byte_length) B.bflags |= WVB_BF_DSD_PADDED;
             break;
         }
@@ -401,8 +403,10 @@ bool unpack_init(Ctx &c)
             words += stereo ? 2 + 2 * ring : 1 + ring;
             sig = (sig ^ (uint32_t)(uint8_t)c.terms[k]) * 16777619u;
         }
-        B.smem_words = (uint16_t)words;
-        B.terms_sig = sig;
+        if (!(h.flags & F_DSD)) {
+            B.smem_words = (uint16_t)words;
+            B.terms_sig = sig;
+        }
     }
     if (c.have_int32) B.bflags |= WVB_BF_HAS_INT32_INFO;
     if (c.have_float) B.bflags |= WVB_BF_HAS_FLOAT_INFO;

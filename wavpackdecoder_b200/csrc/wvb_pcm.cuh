@@ -752,13 +752,19 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
         }
         int a = 0, b = 0;
         bool ok = act;
-        if (ok) ok = decode_word<HYB, STEREO, 0>(br, w, flags, a);
-        WVB_SYNCWARP();
-        if (STEREO) {
-            if (ok) ok = decode_word<HYB, STEREO, 1>(br, w, flags, b);
+        if (!eof_fault) {
+            if (ok) ok = decode_word<HYB, STEREO, 0>(br, w, flags, a);
             WVB_SYNCWARP();
+            if (STEREO) {
+                if (ok) ok = decode_word<HYB, STEREO, 1>(br, w, flags, b);
+                WVB_SYNCWARP();
+            }
+            if (act && !ok) { // get_words came back short (WordsUtils.cs:323,383,393): the reference still runs the passes and
+                eof_fault = true; // the CRC over the rest of the chunk, reading whatever the caller's buffer held.  We model
+                ok = true;        // those stale entries as zeros (exact for silence, and a CRC mismatch either way otherwise).
+                a = b = 0;
+            }
         }
-        if (act && !ok) eof_fault = true;
         if (ok) {
             decorr_frame<STEREO>(SM, nterms, t, a, b);
             if (joint) { b -= (a >> 1); a += b; } // UnpackUtils.cs:615 (App. E-9)
@@ -768,6 +774,8 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
         if (ok) {
             crc = crc * 3 + a;
             if (STEREO) crc = crc * 3 + b;
+        }
+        if (ok && !eof_fault) {
             if (fast16) {
                 *(uint32_t *)op = ((uint32_t)shl32(a, fx.shift) & 0xffffu) | ((uint32_t)shl32(b, fx.shift) << 16);
             } else {
@@ -784,7 +792,7 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
             }
             op += frame_bytes;
         }
-        if (act && !ok) fault = true;
+        if (act && (!ok || (eof_fault && t + 1 == piece_end))) fault = true;
     }
 
     if (fault) { // mute from the start of the caller chunk that contains the fault (UnpackUtils.cs:649-664, App. E-10)
@@ -806,7 +814,8 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
 
     if (!valid || mute_all) return;
     // check_crc_error, UnpackUtils.cs:1414-1421
-    if (crc != D.crc || eof_fault) rflags |= WVB_RF_CRC_ERROR; // after a short get_words the reference's crc runs over stale buffer contents
+    if (crc != D.crc) rflags |= WVB_RF_CRC_ERROR;
+    if (eof_fault) rflags |= WVB_RF_INEXACT; // crc decision modelled, see the sample loop
     if (GENFIX && !(flags & F_FLOAT) && (D.bflags & WVB_BF_WVX_PRESENT)) {
         if (!wvx_here) rflags |= WVB_RF_INEXACT; // crc_mvx left over from an earlier block
         else if (crc_x != crc_mvx) rflags |= WVB_RF_CRC_ERROR | WVB_RF_CRCX_ERROR;
