@@ -81,6 +81,10 @@ def build_corpus(nfiles, seconds, base_seed, threads, budget_s, pin):
     used = lib.wvenc_build_corpus(C.byref(cfg), n_per, unique, base_seed, threads, slab.ctypes.data, slot * unique, offsets.ctypes.data, fsizes.ctypes.data)
     assert used > 0, "corpus generation overflowed its slab"
     gen_s = time.perf_counter() - t0
+    # table order == slab order (the generator's threads bump-allocate): lets the library pipeline H2D / kernels / D2H by segment
+    srt = np.argsort(offsets[:unique], kind="stable")
+    offsets[:unique] = offsets[:unique][srt]
+    fsizes[:unique] = fsizes[:unique][srt]
     pos = (int(used) + 63) & ~63
     for i in range(unique, nfiles):
         j = i % unique

@@ -95,3 +95,30 @@ def test_dsd_raw_output_format(gpu):
     assert np.array_equal(raw, format_samples(ref, 1, dsd=True))
     (pcm, _, _, _), = _decode([data], 0, 4096, gpu.OUT_PCM)
     assert np.array_equal(pcm, format_samples(ref, 1, dsd=False))
+
+
+def test_wvdemo_loop_through_the_api_mirror(gpu):
+    """WvDemo.cs:110-135 written against the Python mirror: same samples per call, sample index, error count and PCM as the oracle."""
+    from _harness import OracleFile
+    from wavpackdecoder_b200 import wavpack_utils as W
+    cases = corrupt_cases()
+    streams = [make_file(seconds=1.3)[2], make_file(seconds=0.7, channels=1, bits=24)[2], cases[0][1], cases[3][1]]
+    for data in streams:
+        o = OracleFile(data)
+        wpc = W.WavpackOpenFileInput(data)
+        nch = W.WavpackGetReducedChannels(wpc)
+        bps = W.WavpackGetBytesPerSample(wpc)
+        buf = np.zeros(4096 * nch, dtype=np.int32)
+        pcm = np.zeros(4096 * nch * bps, dtype=np.uint8)
+        while True:
+            n = W.WavpackUnpackSamples(wpc, buf, 4096)
+            rn, rbuf = o.unpack(4096, nch)
+            assert n == rn
+            if n == 0:
+                break
+            assert np.array_equal(buf[: n * nch], rbuf[: n * nch])
+            assert W.WavpackFormatSamples(buf, n * nch, bps, pcm)
+            assert np.array_equal(pcm[: n * nch * bps], format_samples(rbuf[: n * nch], bps))
+            assert W.WavpackGetSampleIndex(wpc) == o.lib.rd_get_sample_index(o.ctx)
+            assert W.WavpackGetNumErrors(wpc) == o.lib.rd_get_num_errors(o.ctx)
+        o.close()

@@ -72,6 +72,10 @@ struct wvb_batch {
     std::vector<wvb_block_result> host_results;
     wvb_block_result *pending_results = nullptr; size_t pending_n = 0; bool pending_copy = false;
     int launches = 0;
+    cudaStream_t s_in = nullptr, s_out = nullptr; // copy streams of the pipelined host-buffer path
+    std::vector<cudaEvent_t> seg_ev;
+    std::vector<cudaStream_t> seg_streams; // kernels of different segments run concurrently (a block's decode time is a
+                                           // serial-chain latency, so small launches do not finish sooner than big ones)
     int sm_count = 148;
     size_t smem_optin = 0;
     bool timed = false;
@@ -186,6 +190,10 @@ void wvb_batch_destroy(wvb_batch *b)
     if (b->stream) cudaStreamSynchronize(b->stream);
     cudaFree(b->d_in); cudaFree(b->d_out); cudaFree(b->d_descs); cudaFree(b->d_order); cudaFree(b->d_results);
     for (auto &e : b->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : b->seg_ev) if (e) cudaEventDestroy(e);
+    for (auto &st : b->seg_streams) if (st) cudaStreamDestroy(st);
+    if (b->s_in) cudaStreamDestroy(b->s_in);
+    if (b->s_out) cudaStreamDestroy(b->s_out);
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
 }
@@ -243,6 +251,140 @@ static int upload_table(wvb_batch *b, const wvb_block_desc *descs, size_t nblock
     return WVB_OK;
 }
 
+static int launch_plan(wvb_batch *b, const std::vector<Launch> &plan, const uint8_t *din, uint8_t *dout, int fmt, wvb_block_result *dres, cudaStream_t s)
+{
+    int rc;
+    for (const Launch &L : plan) {
+        if (L.variant == wvb::V_DSD) {
+            if ((rc = wvb::launch_dsd(L.cls, din, b->d_descs, b->d_order + L.first, L.count, dout, fmt, dres, s, b->smem_optin, b->device,
+                                      &b->launches)) != WVB_OK)
+                return set_error(rc, std::string("DSD launch failed (unsupported dsd mode or CUDA error): ") + cudaGetErrorString(cudaGetLastError()));
+            continue;
+        }
+        pcm_kernel_t k = pcm_kernel(L.variant);
+        if (!k || L.cls <= 0 || L.cls > 448) return set_error(WVB_E_ARG, "block needs more decorrelation state than any kernel class provides");
+        size_t smem = (size_t)L.cls * CTA_THREADS * sizeof(int);
+        if (smem > b->smem_optin) return set_error(WVB_E_ARG, "shared memory class exceeds the device limit");
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        unsigned grid = (L.count + CTA_THREADS - 1) / CTA_THREADS;
+        k<<<grid, CTA_THREADS, smem, s>>>(din, b->d_descs, b->d_order + L.first, L.count, dout, fmt == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : fmt, dres);
+        CUDA_TRY(cudaGetLastError());
+        b->launches++;
+    }
+    for (const Launch &L : plan) // 0x55 fill of muted DSD pieces, after every decode thread of this plan has finished
+        if (L.variant == wvb::V_DSD && (rc = wvb::launch_dsd_mute_fix(b->d_descs, b->d_order + L.first, L.count, dout, fmt, dres, s, &b->launches)) != WVB_OK)
+            return set_error(rc, "DSD mute pass failed");
+    return WVB_OK;
+}
+
+// Host-buffer decode of a large table, pipelined: the table is cut into segments of consecutive descriptors; segment k's
+// H2D copy, kernels and D2H copy run on three streams so that copies in both directions overlap the kernels of other
+// segments (PCIe is the end-to-end bound: the PCM leaving the GPU is 2x the compressed bytes entering it).
+static int decode_pipelined(wvb_batch *b, const uint8_t *in, size_t in_bytes, const wvb_block_desc *descs, size_t nblocks, uint8_t *out,
+                            size_t out_bytes, int fmt, wvb_block_result *results, bool *used)
+{
+    *used = false;
+    const int ofmt = fmt == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : fmt;
+    size_t nseg = (in_bytes + out_bytes) / ((size_t)1536 << 20);
+    if (nseg < 2 || nblocks < 4096) return WVB_OK;
+    if (nseg > 16) nseg = 16;
+    struct Seg { size_t first, count; uint64_t in_lo, in_hi, out_lo, out_hi; };
+    std::vector<Seg> segs;
+    const uint64_t total = in_bytes + out_bytes, per = total / nseg + 1;
+    uint64_t acc = 0;
+    Seg cur{0, 0, ~0ull, 0, ~0ull, 0};
+    for (size_t i = 0; i < nblocks; i++) {
+        const wvb_block_desc &d = descs[i];
+        const uint64_t fb = wvb_frame_bytes(&d, ofmt);
+        const uint64_t olo = d.out_offset - (uint64_t)d.gap_before * fb - (uint64_t)(wvb::variant_of(d) == wvb::V_DSD ? d.chunk_samples : 0) * fb;
+        const uint64_t ohi = d.out_offset + (uint64_t)d.block_samples * fb;
+        cur.in_lo = std::min<uint64_t>(cur.in_lo, d.in_offset); cur.in_hi = std::max<uint64_t>(cur.in_hi, d.in_offset + d.in_bytes);
+        cur.out_lo = std::min<uint64_t>(cur.out_lo, std::min(olo, d.out_offset)); cur.out_hi = std::max(cur.out_hi, ohi);
+        cur.count++;
+        acc += d.in_bytes + (ohi - d.out_offset);
+        if (acc >= per || i + 1 == nblocks) {
+            segs.push_back(cur);
+            cur = Seg{i + 1, 0, ~0ull, 0, ~0ull, 0};
+            acc = 0;
+        }
+    }
+    // the segments must tile the slabs: inputs nearly disjoint (files laid out in table order), outputs strictly disjoint
+    uint64_t in_sum = 0;
+    for (size_t k = 0; k < segs.size(); k++) {
+        in_sum += segs[k].in_hi - segs[k].in_lo;
+        if (k && segs[k].out_lo < segs[k - 1].out_hi) return WVB_OK;
+        if (segs[k].out_hi > out_bytes || segs[k].in_hi > in_bytes) return WVB_OK;
+    }
+    if (in_sum > in_bytes + in_bytes / 4) return WVB_OK;
+
+    int rc;
+    if (!b->s_in) CUDA_TRY(cudaStreamCreateWithFlags(&b->s_in, cudaStreamNonBlocking));
+    if (!b->s_out) CUDA_TRY(cudaStreamCreateWithFlags(&b->s_out, cudaStreamNonBlocking));
+    while (b->seg_streams.size() < segs.size()) {
+        cudaStream_t st;
+        CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        b->seg_streams.push_back(st);
+    }
+    while (b->seg_ev.size() < 2 * segs.size() + 2) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        b->seg_ev.push_back(e);
+    }
+    if ((rc = ensure(b->d_in, b->d_in_cap, in_bytes + 64)) != WVB_OK) return rc;
+    if ((rc = ensure(b->d_out, b->d_out_cap, out_bytes + 64)) != WVB_OK) return rc;
+    if ((rc = ensure(b->d_results, b->d_results_cap, nblocks + 1)) != WVB_OK) return rc;
+    if ((rc = ensure(b->d_descs, b->d_descs_cap, nblocks + 1)) != WVB_OK) return rc;
+    if ((rc = ensure(b->d_order, b->d_order_cap, nblocks + 1)) != WVB_OK) return rc;
+    cudaStream_t s = b->stream;
+
+    // per-segment plans over one shared order array
+    b->order.resize(nblocks);
+    std::vector<std::vector<Launch>> plans(segs.size());
+    {
+        std::vector<uint32_t> tmp;
+        for (size_t k = 0; k < segs.size(); k++) {
+            make_plan(descs + segs[k].first, segs[k].count, tmp, plans[k]);
+            for (size_t j = 0; j < tmp.size(); j++) b->order[segs[k].first + j] = (uint32_t)(tmp[j] + segs[k].first);
+            for (Launch &L : plans[k]) L.first += (uint32_t)segs[k].first;
+        }
+    }
+    b->plan.clear();
+    b->prepared = false;
+    CUDA_TRY(cudaEventRecord(b->ev[0], s));
+    CUDA_TRY(cudaMemcpyAsync(b->d_descs, descs, nblocks * sizeof(wvb_block_desc), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(b->d_order, b->order.data(), nblocks * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaEventRecord(b->seg_ev[2 * segs.size()], s));
+    CUDA_TRY(cudaStreamWaitEvent(b->s_in, b->seg_ev[2 * segs.size()], 0));
+    CUDA_TRY(cudaEventRecord(b->ev[1], s));
+    for (size_t k = 0; k < segs.size(); k++) {
+        const Seg &g = segs[k];
+        cudaStream_t ks = b->seg_streams[k];
+        CUDA_TRY(cudaMemcpyAsync(b->d_in + g.in_lo, in + g.in_lo, g.in_hi - g.in_lo, cudaMemcpyHostToDevice, b->s_in));
+        CUDA_TRY(cudaEventRecord(b->seg_ev[2 * k], b->s_in));
+        CUDA_TRY(cudaStreamWaitEvent(ks, b->seg_ev[2 * k], 0));
+        if ((rc = launch_plan(b, plans[k], b->d_in, b->d_out, fmt, b->d_results, ks)) != WVB_OK) return rc;
+        CUDA_TRY(cudaEventRecord(b->seg_ev[2 * k + 1], ks));
+        CUDA_TRY(cudaStreamWaitEvent(b->s_out, b->seg_ev[2 * k + 1], 0));
+        CUDA_TRY(cudaStreamWaitEvent(s, b->seg_ev[2 * k + 1], 0));
+        CUDA_TRY(cudaMemcpyAsync(out + g.out_lo, b->d_out + g.out_lo, g.out_hi - g.out_lo, cudaMemcpyDeviceToHost, b->s_out));
+    }
+    CUDA_TRY(cudaEventRecord(b->ev[2], s));
+    CUDA_TRY(cudaEventRecord(b->seg_ev[2 * segs.size() + 1], b->s_out));
+    CUDA_TRY(cudaStreamWaitEvent(s, b->seg_ev[2 * segs.size() + 1], 0));
+    b->pending_copy = false;
+    if (results) {
+        b->host_results.resize(nblocks);
+        CUDA_TRY(cudaMemcpyAsync(b->host_results.data(), b->d_results, nblocks * sizeof(wvb_block_result), cudaMemcpyDeviceToHost, s));
+        b->pending_results = results;
+        b->pending_n = nblocks;
+        b->pending_copy = true;
+    }
+    CUDA_TRY(cudaEventRecord(b->ev[3], s));
+    b->timed = true;
+    *used = true;
+    return WVB_OK;
+}
+
 int wvb_batch_prepare(wvb_batch *b, const wvb_block_desc *descs, size_t nblocks, int out_format)
 {
     if (!b || !descs) return WVB_E_ARG;
@@ -277,6 +419,12 @@ int wvb_batch_decode(wvb_batch *b, const uint8_t *in, size_t in_bytes, const wvb
         if ((rc = validate_table(descs, nblocks, in_bytes, out_bytes, out_format)) != WVB_OK) return rc;
     }
 
+    if (descs && !(mem_flags & (WVB_IN_DEVICE | WVB_OUT_DEVICE | WVB_RESULTS_DEVICE))) {
+        bool used = false;
+        if ((rc = decode_pipelined(b, in, in_bytes, descs, nblocks, (uint8_t *)out, out_bytes, out_format, results, &used)) != WVB_OK) return rc;
+        if (used) return (mem_flags & WVB_NO_SYNC) ? WVB_OK : wvb_batch_wait(b);
+    }
+
     CUDA_TRY(cudaEventRecord(b->ev[0], s));
     const uint8_t *din = in;
     if (!(mem_flags & WVB_IN_DEVICE)) {
@@ -300,27 +448,7 @@ int wvb_batch_decode(wvb_batch *b, const uint8_t *in, size_t in_bytes, const wvb
     if (descs && (rc = upload_table(b, descs, nblocks)) != WVB_OK) return rc;
     CUDA_TRY(cudaEventRecord(b->ev[1], s));
 
-    const int fmt = out_format;
-    for (const Launch &L : b->plan) {
-        if (L.variant == wvb::V_DSD) {
-            if ((rc = wvb::launch_dsd(L.cls, din, b->d_descs, b->d_order + L.first, L.count, dout, fmt, dres, s, b->smem_optin, b->device,
-                                      &b->launches)) != WVB_OK)
-                return set_error(rc, std::string("DSD launch failed (unsupported dsd mode or CUDA error): ") + cudaGetErrorString(cudaGetLastError()));
-            continue;
-        }
-        pcm_kernel_t k = pcm_kernel(L.variant);
-        if (!k || L.cls <= 0 || L.cls > 448) return set_error(WVB_E_ARG, "block needs more decorrelation state than any kernel class provides");
-        size_t smem = (size_t)L.cls * CTA_THREADS * sizeof(int);
-        if (smem > b->smem_optin) return set_error(WVB_E_ARG, "shared memory class exceeds the device limit");
-        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        unsigned grid = (L.count + CTA_THREADS - 1) / CTA_THREADS;
-        k<<<grid, CTA_THREADS, smem, s>>>(din, b->d_descs, b->d_order + L.first, L.count, dout, fmt == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : fmt, dres);
-        CUDA_TRY(cudaGetLastError());
-        b->launches++;
-    }
-    for (const Launch &L : b->plan) // 0x55 fill of muted DSD pieces, after every decode thread has finished
-        if (L.variant == wvb::V_DSD && (rc = wvb::launch_dsd_mute_fix(b->d_descs, b->d_order + L.first, L.count, dout, fmt, dres, s, &b->launches)) != WVB_OK)
-            return set_error(rc, "DSD mute pass failed");
+    if ((rc = launch_plan(b, b->plan, din, dout, out_format, dres, s)) != WVB_OK) return rc;
     CUDA_TRY(cudaEventRecord(b->ev[2], s));
 
     if (!(mem_flags & WVB_OUT_DEVICE)) CUDA_TRY(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, s));

@@ -158,7 +158,7 @@ bool unpack_init(Ctx &c)
     wvb_block_desc &B = c.cur;
     memset(&B, 0, sizeof(B));
     B.in_offset = h.pos;
-    B.in_bytes = h.ckSize + 8;
+    B.in_bytes = (uint32_t)std::min<uint64_t>((uint64_t)h.ckSize + 8, c.len - h.pos); // a truncated last block is still decoded (muted)
     B.block_samples = h.block_samples;
     B.flags = h.flags;
     B.crc = h.crc;
@@ -514,7 +514,7 @@ void index_reference_order(Ctx &c, uint32_t chunk, Sink &out)
             B = c.cur;
         else { // reached without unpack_init (after a gap): decoder state is whatever the previous block left
             memset(&B, 0, sizeof(B));
-            B.in_offset = h.pos; B.in_bytes = h.ckSize + 8; B.block_samples = h.block_samples; B.flags = h.flags; B.crc = h.crc;
+            B.in_offset = h.pos; B.in_bytes = (uint32_t)std::min<uint64_t>((uint64_t)h.ckSize + 8, c.len - h.pos); B.block_samples = h.block_samples; B.flags = h.flags; B.crc = h.crc;
             B.block_index = h.block_index; B.version = (uint16_t)h.version;
             B.bflags = WVB_BF_MUTE_ALL;
         }
