@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -42,8 +43,8 @@ struct SharedColumn { // word i of this thread's column; [slot][thread] layout
     __device__ __forceinline__ int &operator()(int i) { return base[i * CTA_THREADS]; }
 };
 
-template <bool STEREO, bool HYB, bool GENFIX>
-__global__ void __launch_bounds__(CTA_THREADS)
+template <bool STEREO, bool HYB, bool GENFIX, class DEC, int MINB = 0>
+__global__ void __launch_bounds__(CTA_THREADS, MINB)
 k_decode_pcm(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ descs, const uint32_t *__restrict__ order,
              uint32_t count, uint8_t *__restrict__ out, int out_format, wvb_block_result *__restrict__ results)
 {
@@ -52,8 +53,13 @@ k_decode_pcm(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ 
     const bool valid = i < count; // lanes past the end keep running (with no work): the decode loop is warp-synchronous
     const uint32_t bi = order[valid ? i : count - 1];
     SharedColumn SM{smem + threadIdx.x};
-    wvb::decode_block_pcm<STEREO, HYB, GENFIX>(SM, in, descs[bi], out, out_format, &results[bi], valid);
+    wvb::decode_block_pcm<STEREO, HYB, GENFIX, SharedColumn, DEC>(SM, in, descs[bi], out, out_format, &results[bi], valid);
 }
+
+using GenS = wvb::GenericDecorr<true>;
+using GenM = wvb::GenericDecorr<false>;
+using FixS = wvb::FixedDecorr<true, WVB_FIXED_STEREO_TERMS>;
+using FixM = wvb::FixedDecorr<false, WVB_FIXED_MONO_TERMS>;
 
 } // namespace
 
@@ -99,12 +105,21 @@ typedef void (*pcm_kernel_t)(const uint8_t *, const wvb_block_desc *, const uint
 pcm_kernel_t pcm_kernel(int variant)
 {
     switch (variant) {
-    case wvb::V_MONO: return k_decode_pcm<false, false, false>;
-    case wvb::V_STEREO: return k_decode_pcm<true, false, false>;
-    case wvb::V_MONO | wvb::V_GENFIX: return k_decode_pcm<false, false, true>;
-    case wvb::V_STEREO | wvb::V_GENFIX: return k_decode_pcm<true, false, true>;
-    case wvb::V_MONO | wvb::V_GENFIX | wvb::V_HYBRID: return k_decode_pcm<false, true, true>;
-    case wvb::V_STEREO | wvb::V_GENFIX | wvb::V_HYBRID: return k_decode_pcm<true, true, true>;
+    case wvb::V_MONO: return k_decode_pcm<false, false, false, GenM>;
+    case wvb::V_STEREO: return k_decode_pcm<true, false, false, GenS>;
+    case wvb::V_MONO | wvb::V_FIXED: return k_decode_pcm<false, false, false, FixM>;
+    case wvb::V_STEREO | wvb::V_FIXED: {
+        static const int occ = getenv("WVB_FIXED_OCC") ? atoi(getenv("WVB_FIXED_OCC")) : 0; // tuning knob: resident CTAs/SM to compile for
+        if (occ == 6) return k_decode_pcm<true, false, false, FixS, 6>;
+        if (occ == 7) return k_decode_pcm<true, false, false, FixS, 7>;
+        if (occ == 8) return k_decode_pcm<true, false, false, FixS, 8>;
+        if (occ == 10) return k_decode_pcm<true, false, false, FixS, 10>;
+        return k_decode_pcm<true, false, false, FixS>;
+    }
+    case wvb::V_MONO | wvb::V_GENFIX: return k_decode_pcm<false, false, true, GenM>;
+    case wvb::V_STEREO | wvb::V_GENFIX: return k_decode_pcm<true, false, true, GenS>;
+    case wvb::V_MONO | wvb::V_GENFIX | wvb::V_HYBRID: return k_decode_pcm<false, true, true, GenM>;
+    case wvb::V_STEREO | wvb::V_GENFIX | wvb::V_HYBRID: return k_decode_pcm<true, true, true, GenS>;
     default: return nullptr;
     }
 }

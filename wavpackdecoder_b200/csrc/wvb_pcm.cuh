@@ -443,6 +443,141 @@ template <bool STEREO, class SMEM> WVB_DEV void truncate_weights(SMEM &SM, int n
     }
 }
 
+
+// ---- decorrelator policies -------------------------------------------------------------------
+// GenericDecorr: any term list, state in the thread's shared-memory column (decorr_frame above).
+template <bool STEREO> struct GenericDecorr {
+    static constexpr bool kFixed = false;
+    template <class SMEM> WVB_DEV bool load(SMEM &, int) { return true; }
+    template <class SMEM> WVB_DEV void frame(SMEM &SM, int nterms, uint32_t t, int &a, int &b) { decorr_frame<STEREO>(SM, nterms, t, a, b); }
+    template <class SMEM> WVB_DEV void truncate(SMEM &SM, int nterms) { truncate_weights<STEREO>(SM, nterms); }
+};
+
+// FixedDecorr: a compile-time term list (decoder order).  Weights and history live in registers: after unrolling every
+// index below is a constant, so the arrays are scalarised.  History h[j] = x[t-1-j] is a shift register.
+template <bool STEREO, int... TERMS> struct FixedDecorr {
+    static constexpr bool kFixed = true;
+    static constexpr int N = (int)sizeof...(TERMS);
+    int wA[N], wB[N], dl[N];
+    int hA[N][8], hB[N][8];
+
+    static constexpr int term_at(int p)
+    {
+        constexpr int T[N] = {TERMS...};
+        return T[p];
+    }
+    static constexpr int depth(int term) { return term > 8 ? 2 : term < 0 ? 1 : term; }
+
+    // pull the state the generic metadata parser left in shared memory; false if this block's terms differ from TERMS
+    template <class SMEM> WVB_DEV bool load(SMEM &SM, int nterms)
+    {
+        bool match = nterms == N;
+#pragma unroll
+        for (int p = 0; p < N; ++p) {
+            constexpr int T[N] = {TERMS...};
+            const int term = T[p];
+            const uint32_t d = match ? (uint32_t)SM(p) : 0u;
+            if ((int)(d & 31u) - 5 != term) match = false;
+            const int mask = (int)((d >> 8) & 7u), base = (int)(d >> 16);
+            dl[p] = (int)((d >> 5) & 7u);
+            wA[p] = match ? SM(base) : 0;
+            wB[p] = (STEREO && match) ? SM(base + 1) : 0;
+            const int hb = base + (STEREO ? 2 : 1);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                hA[p][j] = 0;
+                hB[p][j] = 0;
+                if (j < depth(term) && match) {
+                    if (term < 0) { // -1: prev B out; -2: prev A out; -3: slot 0 = prev B out, slot 1 = prev A out
+                        hA[p][0] = SM(hb);
+                        if (term == -3) hB[p][0] = SM(hb + 1);
+                    } else {
+                        hA[p][j] = SM(hb + ((-1 - j) & mask)); // x[-1-j] lives in ring slot (-1-j) & mask
+                        if (STEREO) hB[p][j] = SM(hb + mask + 1 + ((-1 - j) & mask));
+                    }
+                }
+            }
+        }
+        return match;
+    }
+
+    template <int TERM> WVB_DEV static int predict(const int *h)
+    {
+        if (TERM == 17) return 2 * h[0] - h[1];
+        if (TERM == 18) return (3 * h[0] - h[1]) >> 1;
+        return h[TERM - 1];
+    }
+    template <int TERM> WVB_DEV static void push(int *h, int v)
+    {
+        constexpr int n = TERM > 8 ? 2 : TERM;
+#pragma unroll
+        for (int j = n - 1; j > 0; --j) h[j] = h[j - 1];
+        h[0] = v;
+    }
+
+    template <int P, class SMEM> WVB_DEV void pass(int &a, int &b)
+    {
+        constexpr int T[N] = {TERMS...};
+        constexpr int term = T[P];
+        const int delta = dl[P];
+        if (term > 0) {
+            int s = predict<term>(hA[P]);
+            const int oa = a + apply_weight(wA[P], s);
+            wA[P] = upd_weight(wA[P], delta, s, a);
+            push<term>(hA[P], oa);
+            a = oa;
+            if (STEREO) {
+                s = predict<term>(hB[P]);
+                const int ob = b + apply_weight(wB[P], s);
+                wB[P] = upd_weight(wB[P], delta, s, b);
+                push<term>(hB[P], ob);
+                b = ob;
+            }
+        } else if (term == -1) {
+            const int s = hA[P][0];
+            const int oa = a + apply_weight(wA[P], s);
+            wA[P] = upd_weight_clip(wA[P], delta, s, a);
+            const int ob = b + apply_weight(wB[P], oa);
+            wB[P] = upd_weight_clip(wB[P], delta, oa, b);
+            hA[P][0] = ob;
+            a = oa; b = ob;
+        } else if (term == -2) {
+            const int s = hA[P][0];
+            const int ob = b + apply_weight(wB[P], s);
+            wB[P] = upd_weight_clip(wB[P], delta, s, b);
+            const int oa = a + apply_weight(wA[P], ob);
+            wA[P] = upd_weight_clip(wA[P], delta, ob, a);
+            hA[P][0] = oa;
+            a = oa; b = ob;
+        } else {
+            const int sA = hA[P][0], sB = hB[P][0];
+            const int oa = a + apply_weight(wA[P], sA);
+            wA[P] = upd_weight_clip(wA[P], delta, sA, a);
+            const int ob = b + apply_weight(wB[P], sB);
+            wB[P] = upd_weight_clip(wB[P], delta, sB, b);
+            hA[P][0] = ob;
+            hB[P][0] = oa;
+            a = oa; b = ob;
+        }
+    }
+    template <int P, class SMEM> WVB_DEV void passes(int &a, int &b)
+    {
+        if constexpr (P < N) {
+            pass<P, SMEM>(a, b);
+            passes<P + 1, SMEM>(a, b);
+        }
+    }
+    template <class SMEM> WVB_DEV void frame(SMEM &, int, uint32_t, int &a, int &b) { passes<0, SMEM>(a, b); }
+    template <class SMEM> WVB_DEV void truncate(SMEM &, int)
+    {
+#pragma unroll
+        for (int p = 0; p < N; ++p) {
+            wA[p] = (int)(int16_t)wA[p];
+            if (STEREO) wB[p] = (int)(int16_t)wB[p];
+        }
+    }
+};
+
 // ---- fixup (UnpackUtils.cs:1251-1404, FloatUtils.cs:32-56) -----------------------------------
 struct Fixup {
     int mode;  // 0 shift only, 1 float, 2 int32+wvx, 3 int32 redundancy only (no wvx)
@@ -551,7 +686,7 @@ WVB_DEV void store_unit(uint8_t *q, int v, int unit, int add128)
 
 // ---- the per-thread block decoder ------------------------------------------------------------
 // STEREO: two coded channels (neither MONO_FLAG nor FALSE_STEREO).  HYB: HYBRID_FLAG.  GENFIX: float / int32 / hybrid fixup.
-template <bool STEREO, bool HYB, bool GENFIX, class SMEM>
+template <bool STEREO, bool HYB, bool GENFIX, class SMEM, class DEC = GenericDecorr<STEREO>>
 WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc &D, uint8_t *out, int out_format, wvb_block_result *res,
                               bool valid = true)
 {
@@ -560,7 +695,7 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
     // lanes without a block (tail of the grid) and MUTE_ALL blocks stay in the warp with n == 0: every lane must reach
     // the warp-wide operations of the sample loop
     const bool mute_all = (D.bflags & WVB_BF_MUTE_ALL) != 0;
-    const uint32_t n = (valid && !mute_all) ? D.block_samples : 0;
+    uint32_t n = (valid && !mute_all) ? D.block_samples : 0;
     const int unit = out_format == WVB_OUT_INT32 ? 4 : (int)D.out_bps;
     const int add128 = (out_format == WVB_OUT_PCM && unit == 1) ? 128 : 0;
     const uint32_t frame_bytes = (uint32_t)unit * D.out_stride;
@@ -660,6 +795,9 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
         }
     }
 
+    DEC dec;
+    const bool terms_ok = dec.load(SM, nterms); // fixed-list kernels refuse (loudly) a block whose terms differ
+    if (!terms_ok) n = 0;
     Words<HYB> w;
     {
         const uint8_t *ep = blk + D.sub_off[WVB_SUB_ENTROPY];
@@ -742,13 +880,13 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
         const bool act = t < n && !fault;
         if (act) {
             if (t == piece_end) {
-                truncate_weights<STEREO>(SM, nterms);
+                dec.truncate(SM, nterms);
                 piece_start = t;
                 const uint32_t rest = n - t;
                 piece_end = t + (chunk < rest ? chunk : rest);
                 trunc8 = (STEREO && piece_end - piece_start >= 16) ? piece_start + 8 : 0xffffffffu;
             } else if (t == trunc8)
-                truncate_weights<STEREO>(SM, nterms);
+                dec.truncate(SM, nterms);
         }
         int a = 0, b = 0;
         bool ok = act;
@@ -766,7 +904,7 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
             }
         }
         if (ok) {
-            decorr_frame<STEREO>(SM, nterms, t, a, b);
+            dec.frame(SM, nterms, t, a, b);
             if (joint) { b -= (a >> 1); a += b; } // UnpackUtils.cs:615 (App. E-9)
             const int aa = a < 0 ? -a : a, ab = b < 0 ? -b : b;
             if (aa > mute_limit || (STEREO && ab > mute_limit)) ok = false;
@@ -813,6 +951,10 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
         res->mute_from = n;
 
     if (!valid || mute_all) return;
+    if (!terms_ok) { // planner routed the block to a kernel specialised for another term list (hash collision): never silent
+        res->crc = -1; res->crc_x = -1; res->mute_from = 0; res->rflags = WVB_RF_BAD_BLOCK;
+        return;
+    }
     // check_crc_error, UnpackUtils.cs:1414-1421
     if (crc != D.crc) rflags |= WVB_RF_CRC_ERROR;
     if (eof_fault) rflags |= WVB_RF_INEXACT; // crc decision modelled, see the sample loop

@@ -7,7 +7,24 @@
 namespace wvb {
 
 // kernel variants of the PCM path
-enum { V_MONO = 0, V_STEREO = 1, V_GENFIX = 2, V_HYBRID = 4, V_DSD = 8, V_COUNT = 16 };
+enum { V_MONO = 0, V_STEREO = 1, V_GENFIX = 2, V_HYBRID = 4, V_DSD = 8, V_FIXED = 16, V_COUNT = 32 };
+
+// FNV-1a over the term list in DECODER order, as wvb_index computes wvb_block_desc.terms_sig
+constexpr uint32_t terms_hash(const int *t, int n)
+{
+    uint32_t sig = 2166136261u;
+    for (int k = 0; k < n; k++) sig = (sig ^ (uint32_t)(uint8_t)t[k]) * 16777619u;
+    return sig;
+}
+
+// Term lists with an in-register kernel (decoder order = reverse of the file/encoder order).
+//   stereo {18,18,2,3,-2}: WavPack's default-mode list (BASELINE configs[0]/[1]);  mono {18,18,2,3}: the same without the cross term
+#define WVB_FIXED_STEREO_TERMS -2, 3, 2, 18, 18
+#define WVB_FIXED_MONO_TERMS 3, 2, 18, 18
+constexpr int kFixedStereo[] = {WVB_FIXED_STEREO_TERMS};
+constexpr int kFixedMono[] = {WVB_FIXED_MONO_TERMS};
+constexpr uint32_t kFixedStereoSig = terms_hash(kFixedStereo, 5);
+constexpr uint32_t kFixedMonoSig = terms_hash(kFixedMono, 4);
 
 inline int variant_of(const wvb_block_desc &d)
 {
@@ -15,6 +32,11 @@ inline int variant_of(const wvb_block_desc &d)
     int v = (d.flags & (4u | 0x40000000u)) ? V_MONO : V_STEREO;
     if (d.flags & 8u) v |= V_HYBRID | V_GENFIX;
     else if ((d.flags & (0x80u | 0x100u)) || (d.bflags & WVB_BF_WVX_PRESENT)) v |= V_GENFIX;
+    else if (!(d.bflags & (WVB_BF_MUTE_ALL | WVB_BF_STALE_STATE))) {
+        // plain lossless block: use the in-register kernel when its term list is one we specialise (checked again on the device)
+        if (v == V_STEREO && d.sub_len[WVB_SUB_TERMS] == 5 && d.terms_sig == kFixedStereoSig) v |= V_FIXED;
+        if (v == V_MONO && d.sub_len[WVB_SUB_TERMS] == 4 && d.terms_sig == kFixedMonoSig) v |= V_FIXED;
+    }
     return v;
 }
 
