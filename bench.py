@@ -231,6 +231,7 @@ def workload_config(args, corpus, nblocks):
     cfg = {
         "workload": "BASELINE configs[1]: batch of %d synthetic 16-bit stereo 44.1 kHz default-mode .wv files x %.0f s per GPU, one WavPack block per thread" % (args.files, args.seconds),
         "files_per_gpu": args.files, "seconds_per_file": args.seconds, "block_samples": 22050,
+        "files_per_gpu_requested": getattr(args, "requested_files", args.files),
         "unique_files_per_gpu": corpus["unique"] if corpus else None,
         "l2_policy": "inputs (compressed slab + PCM output, GBs) far larger than the 126 MB L2; no flush needed",
         "chunk_samples": 4096,
@@ -282,6 +283,18 @@ def main():
         torch.cuda.synchronize()
 
     threads = max(1, host_cores() // max(1, world))
+    # host RAM guard: the e2e leg pins the compressed slab and the PCM output of the whole per-GPU batch (~2.9 MB per 10 s file)
+    requested_files = args.files
+    args.requested_files = requested_files
+    try:
+        avail = [int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0]
+        per_file = int(args.seconds * 44100 * 4 * 1.55) + 65536
+        cap = int(0.7 * avail / max(1, world) / per_file)
+        if cap < args.files:
+            args.files = max(64, cap)
+            log("host RAM guard: files per GPU reduced %d -> %d (MemAvailable %.0f GB, %d ranks)" % (requested_files, args.files, avail / 1e9, world))
+    except Exception:
+        pass
     t0 = time.perf_counter()
     corpus = build_corpus(args.files, args.seconds, 0x5EED0000 + rank * args.files, threads, args.gen_budget_s, pin=True)
     log("corpus: %d files (%d unique) %.2f GB compressed, generated in %.1f s (+%.1f s total) on %d threads" % (
@@ -338,10 +351,8 @@ def main():
     torch.cuda.synchronize()
     elapsed = time.perf_counter() - t0
     clk = clocks.stop()
-    t = torch.tensor([elapsed], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_max = float(t.item())
+    from wavpackdecoder_b200.sharding import max_over_ranks
+    elapsed_max = max_over_ranks(elapsed, dev)
     value = total_samples * world * args.steps / elapsed_max
 
     # ---- e2e: host buffers through the public C-ABI call, index pass + H2D + kernels + D2H every step ----
@@ -364,11 +375,9 @@ def main():
             c2 = step_e2e()
         torch.cuda.synchronize()
         e_elapsed = time.perf_counter() - t0
-        t = torch.tensor([e_elapsed], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_elapsed_max = max_over_ranks(e_elapsed, dev)
         e2e_ok = all((results[i].rflags == 0) for i in range(0, cp.nblocks, max(1, cp.nblocks // 1000)))
-        e2e = {"value": total_samples * world * args.steps / float(t.item()), "unit": UNIT,
+        e2e = {"value": total_samples * world * args.steps / e_elapsed_max, "unit": UNIT,
                "h2d_bytes_per_step": int(slab.size + cp.nblocks * (144 + 4)), "d2h_bytes_per_step": int(pcm_bytes + cp.nblocks * 16),
                "includes": "host block-index pass + H2D + kernels + D2H", "validated": bool(e2e_ok)}
 
