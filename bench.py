@@ -388,8 +388,9 @@ def main():
     achieved = algo_bytes / (k_ms * 1e-3) / 1e9
     traffic = ncu_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic.get("dram_bytes_per_launch") if traffic else None, "peak_kind": peak_kind,
-                "kernel": "k_decode_pcm<stereo,lossless>", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": int(algo_bytes),
+                "traffic": traffic.get("dram_bytes_per_launch") if traffic and traffic.get("blocks_per_launch") == cp.nblocks else None,
+                "traffic_source": traffic.get("source") if traffic else None, "peak_kind": peak_kind,
+                "kernel": "k_decode_pcm<stereo,lossless,FixedDecorr<-2,3,2,18,18>>", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": int(algo_bytes),
                 "bytes_per_sample": algo_bytes / total_samples}
 
     cpu_baseline = None
