@@ -50,13 +50,13 @@ def host_cores():
 # --------------------------------------------------------------------------------------
 # synthetic corpus
 # --------------------------------------------------------------------------------------
-def build_corpus(nfiles, seconds, base_seed, threads, budget_s, pin):
+def build_corpus(nfiles, seconds, base_seed, threads, budget_s, pin, cfg_kw=None):
     """Encode up to `nfiles` unique files within ~budget_s (the rest are byte copies of earlier files placed at new
     offsets; warps still hold 32 different blocks because replicas are nfiles_unique files apart)."""
     import _harness as H
     import torch
-    cfg = H.make_config()
-    n_per = int(cfg.sample_rate * seconds)
+    cfg = H.make_config(**(cfg_kw or {}))
+    n_per = int(cfg.sample_rate * seconds) * (8 if cfg.kind == H.KIND_DSD else 1)  # DSD: byte-times (8 one-bit samples each)
     lib = H.wvenc()
     # probe: size and speed
     probe_n = max(2, min(threads, nfiles))

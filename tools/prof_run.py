@@ -20,16 +20,24 @@ def main():
     ap.add_argument("--seconds", type=float, default=1.0)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--fmt", default="pcm")
-    ap.add_argument("--kw", nargs="*", default=[])
+    ap.add_argument("--kw", nargs="*", default=[], help="encoder config overrides, e.g. bits=24 channels=6 terms=18,18,2 kind=1")
+    ap.add_argument("--open-flags", type=lambda x: int(x, 0), default=0)
     args = ap.parse_args()
     import torch
     import bench
     from wavpackdecoder_b200 import _native as N
     from wavpackdecoder_b200.batch import BatchDecoder, Corpus
-    corpus = bench.build_corpus(args.files, args.seconds, 0x5EED0000, bench.host_cores(), 30.0, pin=False)
+    kw = {}
+    for item in args.kw:
+        k, v = item.split("=", 1)
+        if k in ("terms", "deltas"):
+            kw[k] = [int(x) for x in v.split(",") if x]
+        else:
+            kw[k] = int(v, 0)
+    corpus = bench.build_corpus(args.files, args.seconds, 0x5EED0000, bench.host_cores(), 30.0, pin=False, cfg_kw=kw)
     slab = corpus["slab"]
     fmt = N.OUT_PCM if args.fmt == "pcm" else N.OUT_INT32
-    cp = Corpus(slab, corpus["offsets"], corpus["sizes"], out_format=fmt)
+    cp = Corpus(slab, corpus["offsets"], corpus["sizes"], out_format=fmt, open_flags=args.open_flags)
     dec = BatchDecoder(0)
     dev = torch.device("cuda", 0)
     d_in = torch.from_numpy(slab).to(dev)
@@ -40,8 +48,9 @@ def main():
     for i in range(args.steps):
         dec.decode(d_in.data_ptr(), slab.size, None, cp.nblocks, d_out.data_ptr(), cp.out_bytes, fmt, FL, d_res.data_ptr())
         tm = dec.timing()
-        print("step %d: kernel %.3f ms, %d blocks, %.3f Gsamples/s, launches %d" % (
-            i, tm["kernel_ms"], cp.nblocks, cp.total_samples / tm["kernel_ms"] / 1e6, tm["launches"]), flush=True)
+        print("step %d: kernel %.3f ms, %d blocks, %.3f Gsamples/s, launches %d, in %.2f GB out %.2f GB -> %.1f GB/s" % (
+            i, tm["kernel_ms"], cp.nblocks, cp.total_samples / tm["kernel_ms"] / 1e6, tm["launches"], corpus["compressed_bytes"] / 1e9,
+            cp.out_bytes / 1e9, (corpus["compressed_bytes"] + cp.out_bytes) / tm["kernel_ms"] / 1e6), flush=True)
     res = d_res.cpu().numpy().view(np.uint32).reshape(-1, 4)
     print("flagged blocks:", int((res[:cp.nblocks, 1] != 0).sum()))
 
