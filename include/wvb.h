@@ -191,7 +191,9 @@ typedef struct wvb_batch wvb_batch;
 int wvb_batch_create(int device, wvb_batch **out);
 void wvb_batch_destroy(wvb_batch *b);
 
-/* Decode nblocks blocks.  `in` holds the compressed slab (descs' in_offset index it), `out`
+/* Decode nblocks blocks.  The slab passed as `in` must have at least 16 readable bytes after the last block (the
+ * kernels fetch whole aligned words one word ahead); host slabs are copied into padded device memory by the library,
+ * device slabs (WVB_IN_DEVICE) must be allocated with that slack.  `in` holds the compressed slab (descs' in_offset index it), `out`
  * receives int32 or packed PCM at descs' out_offset.  Host pointers are copied through the
  * batch's device buffers (pinned host memory makes the copies asynchronous); device pointers
  * (WVB_*_DEVICE) are used in place.  descs is always a host pointer.  results may be NULL. */

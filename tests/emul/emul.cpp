@@ -48,9 +48,8 @@ extern "C" int emul_decode(const uint8_t *in, const wvb_block_desc *descs, size_
                 pt.w.assign(256, 0);
                 wvb::dsd_decode_high(pt, pt0, in, D, out, out_format, &r, true);
             } else if (mode == 1) {
-                std::vector<uint8_t> prob(32 * 256);
                 std::vector<uint16_t> summed(32 * 256);
-                wvb::DsdFastTables T{prob.data(), summed.data()};
+                wvb::DsdFastTables T{summed.data()};
                 const uint8_t *p = in + D.in_offset + D.sub_off[WVB_SUB_DSD];
                 const uint32_t len = D.sub_len[WVB_SUB_DSD];
                 int bins = 1;

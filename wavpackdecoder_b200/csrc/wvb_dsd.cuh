@@ -65,9 +65,7 @@ k_dsd_fast(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ de
     const uint32_t bi = order[w];
     const wvb_block_desc &D = descs[bi];
     DsdFastTables T;
-    uint8_t *base = (uint8_t *)dsd_smem + (size_t)wic * bins_max * 768;
-    T.summed = (uint16_t *)base;
-    T.prob = base + (size_t)bins_max * 512;
+    T.summed = (uint16_t *)((uint8_t *)dsd_smem + (size_t)wic * bins_max * 512);
     const uint8_t *p = in + D.in_offset + D.sub_off[WVB_SUB_DSD];
     const uint32_t len = D.sub_len[WVB_SUB_DSD];
     int bins = 1;
@@ -173,7 +171,7 @@ inline int launch_dsd(int cls, const uint8_t *din, const wvb_block_desc *d_descs
         k_dsd_high<<<(count + DSD_HIGH_THREADS - 1) / DSD_HIGH_THREADS, DSD_HIGH_THREADS, smem, s>>>(din, d_descs, d_order, count, dout, out_format, dres, pt);
     } else if (cls >= 16 && cls <= 16 + 5) {
         const int bins = 1 << (cls - 16);
-        const size_t smem = (size_t)DSD_FAST_WARPS * bins * 768;
+        const size_t smem = (size_t)DSD_FAST_WARPS * bins * 512;
         if (smem > smem_optin) return WVB_E_ARG;
         if (cudaFuncSetAttribute((const void *)k_dsd_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WVB_E_CUDA;
         k_dsd_fast<<<(count + DSD_FAST_WARPS - 1) / DSD_FAST_WARPS, DSD_FAST_WARPS * 32, smem, s>>>(din, d_descs, d_order, count, dout, out_format, dres, bins);

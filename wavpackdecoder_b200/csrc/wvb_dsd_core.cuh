@@ -20,14 +20,38 @@ WVB_DEV int dsd_key_mode(uint32_t k) { return (int)(k & 15u); }
 WVB_DEV int dsd_key_hbits(uint32_t k) { return (int)((k >> 4) & 15u); }
 WVB_DEV int dsd_key_rate(uint32_t k) { return (int)((k >> 8) & 255u); }
 
-// sequential byte source over the ID_DSD_BLOCK payload with the reference's `byteptr < data.Length` guards
+// sequential byte source over the ID_DSD_BLOCK payload with the reference's `byteptr < data.Length` guards.
+// One thread per stream: bytes come out of a 32-bit word fetched one word ahead (the range decoder consumes a byte
+// every few steps; a dependent byte load per renormalisation would put an L2 round trip on the critical path).
 struct ByteReader {
     const uint8_t *p;
     uint32_t pos, len;
-    WVB_DEV void init(const uint8_t *s, uint32_t n, uint32_t at) { p = s; len = n; pos = at; }
+    uint32_t cur, nxt;      // word holding byte `pos`, and the following word
+    const uint8_t *wnext;   // aligned address of the word after nxt
+    WVB_DEV uint32_t fetch()
+    {
+        const uint32_t w = wvb_ld_u32(wnext); // the slab is padded: reading up to 8 bytes past the payload is safe
+        wnext += 4;
+        return w;
+    }
+    WVB_DEV void init(const uint8_t *s, uint32_t n, uint32_t at)
+    {
+        p = s; len = n; pos = at;
+        const uint8_t *a = s + at;
+        wnext = a - ((uintptr_t)a & 3);
+        cur = fetch();
+        nxt = fetch();
+    }
     WVB_DEV bool more() const { return pos < len; }
     WVB_DEV uint32_t left() const { return len - pos; }
-    WVB_DEV uint32_t get() { return wvb_ld_u8(p + pos++); }
+    WVB_DEV uint32_t get()
+    {
+        const uint32_t sh = (uint32_t)((uintptr_t)(p + pos) & 3) * 8;
+        const uint32_t b = (cur >> sh) & 0xffu;
+        pos++;
+        if (sh == 24) { cur = nxt; nxt = fetch(); }
+        return b;
+    }
 };
 
 struct DsdOut { // where the decoded bytes go
@@ -207,9 +231,10 @@ WVB_DEV void dsd_decode_high(SMEM &PT, const int *ptable0, const uint8_t *in, co
 }
 
 // ---- mode 1 ("fast") --------------------------------------------------------------------------
-// Tables for one block: prob[bins*256] bytes and summed[bins*256] u16.  LANES cooperate; on the host LANES == 1.
+// Table for one block: summed[bins*256] u16 cumulative probabilities (the per-symbol probability is the difference of
+// neighbours, so the reference's separate probabilities[] and lookup_buffer[] are not stored: 512 B per history bin).
+// Lanes cooperate on the device; on the host nlanes == 1.
 struct DsdFastTables {
-    uint8_t *prob;
     uint16_t *summed;
 };
 
@@ -231,11 +256,11 @@ WVB_DEV uint32_t dsd_fast_build(const DsdFastTables &T, const uint8_t *p, uint32
             if (code > max_probability) {
                 int z = code - max_probability;
                 while (outp < tot && z-- > 0) {
-                    if ((int)(outp % (uint32_t)nlanes) == lane) T.prob[outp] = 0;
+                    if ((int)(outp % (uint32_t)nlanes) == lane) T.summed[outp] = 0;
                     outp++;
                 }
             } else if (code != 0) {
-                if ((int)(outp % (uint32_t)nlanes) == lane) T.prob[outp] = (uint8_t)code;
+                if ((int)(outp % (uint32_t)nlanes) == lane) T.summed[outp] = (uint16_t)code;
                 outp++;
             } else
                 break;
@@ -243,22 +268,23 @@ WVB_DEV uint32_t dsd_fast_build(const DsdFastTables &T, const uint8_t *p, uint32
         if (outp < tot) return 0;
         if (at < len) at++; // terminator byte (already validated == 0 by the index pass)
     } else {
-        for (uint32_t i = (uint32_t)lane; i < tot; i += (uint32_t)nlanes) T.prob[i] = wvb_ld_u8(p + at + i);
+        for (uint32_t i = (uint32_t)lane; i < tot; i += (uint32_t)nlanes) T.summed[i] = wvb_ld_u8(p + at + i);
         at += tot;
     }
     return at;
 }
 
-// after a barrier: cumulative sums, one bin at a time; each lane owns 256/nlanes consecutive symbols
+// after a barrier: in-place cumulative sums (summed[] holds the raw probabilities on entry), one bin at a time; each lane
+// owns 256/nlanes consecutive symbols
 template <class SCAN> WVB_DEV void dsd_fast_sums(const DsdFastTables &T, int bins, int lane, int nlanes, SCAN scan_exclusive)
 {
     const int per = 256 / nlanes;
     for (int b = 0; b < bins; ++b) {
         uint32_t local = 0;
-        for (int k = 0; k < per; ++k) local += T.prob[b * 256 + lane * per + k];
+        for (int k = 0; k < per; ++k) local += T.summed[b * 256 + lane * per + k];
         uint32_t run = scan_exclusive(local);
         for (int k = 0; k < per; ++k) {
-            run += T.prob[b * 256 + lane * per + k];
+            run += T.summed[b * 256 + lane * per + k];
             T.summed[b * 256 + lane * per + k] = (uint16_t)run;
         }
     }
@@ -295,8 +321,9 @@ WVB_DEV void dsd_fast_decode(const DsdFastTables &T, int bins, const uint8_t *p,
         if (index >= sum) { failed = true; fail_at = j; break; }
         const int code = find(row, index);
         emit(j, code);
-        if (code > 0) rc.low += (uint32_t)row[code - 1] * mult;
-        rc.high = rc.low + (uint32_t)T.prob[p0 * 256 + code] * mult - 1;
+        const uint32_t below = code > 0 ? row[code - 1] : 0u;
+        rc.low += below * mult;
+        rc.high = rc.low + ((uint32_t)row[code] - below) * mult - 1;
         crc = crc * 3 + code;
         if (mono) p0 = code & (bins - 1);
         else { p0 = p1; p1 = code & (bins - 1); }
