@@ -885,6 +885,10 @@ static void encode_pcm_block(encoder *E, stream_state *S, const i32 *srcL, const
     }
     { /* history */
         int k = 0;
+        if (E->version == 0x402 && hybrid) { /* v0x402 hybrid streams carry 2 (mono) / 4 (stereo) extra bytes first (UnpackUtils.cs:277-283) */
+            int pad = stereo ? 4 : 2;
+            for (int q = 0; q < pad; q++) tmp[k++] = 0;
+        }
         int npass = (cfg->extras & WVENC_X_ALL_HISTORY) ? nt : (nt ? 1 : 0);
         for (int q = 0; q < npass; q++) {
             int d = nt - 1 - q;

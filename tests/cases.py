@@ -52,6 +52,20 @@ PCM_CASES = [
     ("extras", 0, 4096, dict(extras=1 | 2 | 4 | 8 | 16 | 32 | 64, sample_rate=37800)),
     ("unknown_len", 0, 4096, dict(unknown_length=1)),
     ("all_hist_same_terms", 0, 4096, dict(extras=128, terms=[2, 2, 2])),
+    ("false_stereo_24bit", 0, 4096, dict(false_stereo=1, bits=24, seconds=1.2)),
+    ("false_stereo_int32_nowvx", 0, 4096, dict(false_stereo=1, bits=32, int32_sent_bits=8, int32_wvx=0, seconds=1.2)),
+    ("false_stereo_float", 0, 4096, dict(false_stereo=1, kind=KIND_FLOAT, bits=32, float_shift=2, seconds=1.2)),
+    ("false_stereo_hybrid", 0, 4096, dict(false_stereo=1, kind=KIND_HYBRID, terms=[18, 2], seconds=1.2)),
+    ("v402_hybrid_history_skip", 0, 4096, dict(kind=KIND_HYBRID, version=0x402, terms=[18, 2])),
+    ("v402_hybrid_mono", 0, 4096, dict(kind=KIND_HYBRID, version=0x402, channels=1, terms=[3])),
+    ("v407", 0, 4096, dict(version=0x407)),
+    ("delta0", 0, 4096, dict(terms=[18, 18, 2, 3, -2], deltas=[0, 0, 0, 0, 0])),
+    ("default_terms_delta5", 0, 4096, dict(terms=[18, 18, 2, 3, -2], deltas=[5, 4, 3, 2, 1])),
+    ("mono_default_terms", 0, 4096, dict(channels=1, terms=[18, 18, 2, 3])),
+    ("terms_minus3_only", 0, 4096, dict(terms=[-3])),
+    ("shift8_24bit", 0, 4096, dict(bits=24, shift=8)),
+    ("hybrid_24bit", 0, 4096, dict(kind=KIND_HYBRID, bits=24, hybrid_bitrate=6 * 256, terms=[18, 18, 2])),
+    ("big_block", 0, 4096, dict(block_samples=88200, seconds=2.0)),
 ]
 
 from _harness import KIND_DSD  # noqa: E402
