@@ -122,3 +122,30 @@ def test_wvdemo_loop_through_the_api_mirror(gpu):
             assert W.WavpackGetSampleIndex(wpc) == o.lib.rd_get_sample_index(o.ctx)
             assert W.WavpackGetNumErrors(wpc) == o.lib.rd_get_num_errors(o.ctx)
         o.close()
+
+
+def test_large_mixed_batch_properties(gpu):
+    """A batch the oracle would take minutes to decode serially: size-independent checks.  Every block's CRC (written by the
+    encoder from the SOURCE samples) must verify on the device, the total sample count must match, and a checksum of
+    per-file checksums must equal the one computed from the encoder-side reconstruction."""
+    import hashlib
+    from wavpackdecoder_b200.batch import BatchDecoder, Corpus
+    kinds = [dict(), dict(channels=1), dict(bits=24), dict(bits=8), dict(terms=[17, 2, -1, 5]), dict(bits=32, int32_sent_bits=8),
+             dict(joint_stereo=0, terms=[18, 18, 2, 3, -2], deltas=[3, 3, 2, 2, 1]), dict(shift=3)]
+    files, expect = [], hashlib.md5()
+    total = 0
+    for i in range(256):
+        cfg, src, data, recon = make_file(seed=0xABC000 + i, seconds=0.5 + 0.25 * (i % 3), want_recon=True, **kinds[i % len(kinds)])
+        files.append(data)
+        expect.update(hashlib.md5(np.ascontiguousarray(recon, dtype="<i4").tobytes()).digest())
+        total += recon.size // cfg.channels
+    cp = Corpus.from_files(files, out_format=gpu.OUT_INT32)
+    dec = BatchDecoder(0)
+    out, results = dec.decode_corpus(cp)
+    dec.close()
+    assert cp.total_samples == total
+    assert all(results[k].rflags == 0 for k in range(cp.nblocks))
+    got = hashlib.md5()
+    for i in range(cp.nfiles):
+        got.update(hashlib.md5(np.ascontiguousarray(cp.file_output(out, i), dtype="<i4").tobytes()).digest())
+    assert got.hexdigest() == expect.hexdigest()

@@ -31,14 +31,57 @@ struct PtableColumn { // ptable entry i of this thread: [256][DSD_HIGH_THREADS]
     __device__ __forceinline__ int &operator()(int i) { return base[i * DSD_HIGH_THREADS]; }
 };
 
+// mode 0 (DsdUtils.cs:73-82) is a copy plus the crc*3+byte recurrence.  One block per warp: lanes read 4 consecutive
+// bytes each (128 B per warp step, coalesced), and the CRC -- an affine recurrence mod 2^32 -- is
+// evaluated per 128-byte step as crc = crc*3^128 + sum_l local_l * 3^(124-4l) with a warp reduction.
+static __device__ __forceinline__ uint32_t pow3(uint32_t e)
+{
+    uint32_t r = 1, b = 3;
+    while (e) { if (e & 1) r *= b; b *= b; e >>= 1; }
+    return r;
+}
+
 static __global__ void __launch_bounds__(DSD_RAW_THREADS)
 k_dsd_raw(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ descs, const uint32_t *__restrict__ order, uint32_t count,
           uint8_t *__restrict__ out, int out_format, wvb_block_result *__restrict__ results)
 {
-    const uint32_t i = blockIdx.x * DSD_RAW_THREADS + threadIdx.x;
-    if (i >= count) return;
-    const uint32_t bi = order[i];
-    dsd_decode_raw(in, descs[bi], out, out_format, &results[bi]);
+    const int lane = threadIdx.x & 31;
+    const uint32_t w = (blockIdx.x * DSD_RAW_THREADS + threadIdx.x) >> 5;
+    if (w >= count) return; // whole warp leaves together
+    const uint32_t bi = order[w];
+    const wvb_block_desc &D = descs[bi];
+    DsdOut o;
+    dsd_out_init(o, D, out, out_format);
+    const uint8_t *p = in + D.in_offset + D.sub_off[WVB_SUB_DSD] + 2;
+    const uint32_t len = D.sub_len[WVB_SUB_DSD];
+    uint32_t total = D.block_samples * (uint32_t)o.coded_ch;
+    if (len - 2 < total) total = len - 2; // DsdUtils.cs:77-78
+    const uint32_t lane_pow = pow3(124u - 4u * (uint32_t)lane), step_pow = pow3(128u);
+    uint32_t crc = 0xffffffffu;
+    const uint32_t full = total & ~127u;
+    // fast path: plain byte output of a stereo (or mono) stream into a contiguous frame layout
+    const bool bytes_contig = o.unit == 1 && o.frame_bytes == (uint32_t)o.coded_ch && o.out_ch == o.coded_ch;
+    for (uint32_t base = 0; base < full; base += 128) {
+        const uint32_t j = base + 4u * (uint32_t)lane;
+        const uint32_t b0 = p[j], b1 = p[j + 1], b2 = p[j + 2], b3 = p[j + 3];
+        const uint32_t local = ((b0 * 3u + b1) * 3u + b2) * 3u + b3;
+        crc = crc * step_pow + __reduce_add_sync(0xffffffffu, local * lane_pow);
+        if (bytes_contig) {
+            uint8_t *q = o.op + j;
+            const uint32_t a = (uint32_t)o.add;
+            q[0] = (uint8_t)(b0 + a); q[1] = (uint8_t)(b1 + a); q[2] = (uint8_t)(b2 + a); q[3] = (uint8_t)(b3 + a);
+        } else {
+            o.put(j, (int)b0); o.put(j + 1, (int)b1); o.put(j + 2, (int)b2); o.put(j + 3, (int)b3);
+        }
+    }
+    if (lane == 0) { // tail (< 128 values) and the verdict
+        for (uint32_t j = full; j < total; ++j) {
+            const uint32_t b = p[j];
+            crc = crc * 3u + b;
+            o.put(j, (int)b);
+        }
+        dsd_finish(D, &results[bi], (int)crc, false, 0, 0);
+    }
 }
 
 static __global__ void __launch_bounds__(DSD_HIGH_THREADS)
@@ -161,7 +204,7 @@ inline int launch_dsd(int cls, const uint8_t *din, const wvb_block_desc *d_descs
 {
     if (count == 0) return WVB_OK;
     if (cls == 0) {
-        k_dsd_raw<<<(count + DSD_RAW_THREADS - 1) / DSD_RAW_THREADS, DSD_RAW_THREADS, 0, s>>>(din, d_descs, d_order, count, dout, out_format, dres);
+        k_dsd_raw<<<(count + DSD_RAW_THREADS / 32 - 1) / (DSD_RAW_THREADS / 32), DSD_RAW_THREADS, 0, s>>>(din, d_descs, d_order, count, dout, out_format, dres);
     } else if (cls == 3) {
         const int *pt = dsd_device_ptables(device);
         if (!pt) return WVB_E_CUDA;
