@@ -75,6 +75,7 @@ struct wvb_batch {
     std::vector<uint32_t> order;
     std::vector<Launch> plan;
     size_t prepared_n = 0; bool prepared = false; int prepared_fmt = -1;
+    uint64_t prepared_in_extent = 0, prepared_out_extent = 0; // slab sizes the prepared table needs
     std::vector<wvb_block_result> host_results;
     wvb_block_result *pending_results = nullptr; size_t pending_n = 0; bool pending_copy = false;
     int launches = 0;
@@ -102,18 +103,21 @@ template <class T> int ensure(T *&p, size_t &cap, size_t need)
 
 typedef void (*pcm_kernel_t)(const uint8_t *, const wvb_block_desc *, const uint32_t *, uint32_t, uint8_t *, int, wvb_block_result *);
 
-pcm_kernel_t pcm_kernel(int variant)
+pcm_kernel_t pcm_kernel(int variant, uint32_t count = 0, int sm_count = 148)
 {
     switch (variant) {
     case wvb::V_MONO: return k_decode_pcm<false, false, false, GenM>;
     case wvb::V_STEREO: return k_decode_pcm<true, false, false, GenS>;
     case wvb::V_MONO | wvb::V_FIXED: return k_decode_pcm<false, false, false, FixM>;
     case wvb::V_STEREO | wvb::V_FIXED: {
-        static const int occ = getenv("WVB_FIXED_OCC") ? atoi(getenv("WVB_FIXED_OCC")) : 0; // tuning knob: resident CTAs/SM to compile for
+        // Two builds of the same kernel: 91 registers (5 CTAs/SM, no spills) and, compiled for 6 resident CTAs/SM, 80 registers
+        // with ~50 B of spills.  The second wins once the launch no longer fits one wave of the first (measured on B200:
+        // 200k blocks 114.5 -> 108.4 ms; 80k blocks 49.2 vs 52.7 ms).  WVB_FIXED_OCC overrides for experiments.
+        static const int env_occ = getenv("WVB_FIXED_OCC") ? atoi(getenv("WVB_FIXED_OCC")) : -1;
+        const int occ = env_occ >= 0 ? env_occ : (count > (uint32_t)sm_count * 5u * CTA_THREADS ? 6 : 0);
         if (occ == 6) return k_decode_pcm<true, false, false, FixS, 6>;
         if (occ == 7) return k_decode_pcm<true, false, false, FixS, 7>;
         if (occ == 8) return k_decode_pcm<true, false, false, FixS, 8>;
-        if (occ == 10) return k_decode_pcm<true, false, false, FixS, 10>;
         return k_decode_pcm<true, false, false, FixS>;
     }
     case wvb::V_MONO | wvb::V_GENFIX: return k_decode_pcm<false, false, true, GenM>;
@@ -276,7 +280,7 @@ static int launch_plan(wvb_batch *b, const std::vector<Launch> &plan, const uint
                 return set_error(rc, std::string("DSD launch failed (unsupported dsd mode or CUDA error): ") + cudaGetErrorString(cudaGetLastError()));
             continue;
         }
-        pcm_kernel_t k = pcm_kernel(L.variant);
+        pcm_kernel_t k = pcm_kernel(L.variant, L.count, b->sm_count);
         if (!k || L.cls <= 0 || L.cls > 448) return set_error(WVB_E_ARG, "block needs more decorrelation state than any kernel class provides");
         size_t smem = (size_t)L.cls * CTA_THREADS * sizeof(int);
         if (smem > b->smem_optin) return set_error(WVB_E_ARG, "shared memory class exceeds the device limit");
@@ -410,6 +414,13 @@ int wvb_batch_prepare(wvb_batch *b, const wvb_block_desc *descs, size_t nblocks,
     if (rc != WVB_OK) return rc;
     if ((rc = upload_table(b, descs, nblocks)) != WVB_OK) return rc;
     CUDA_TRY(cudaStreamSynchronize(b->stream));
+    b->prepared_in_extent = b->prepared_out_extent = 0;
+    for (size_t i = 0; i < nblocks; i++) {
+        const wvb_block_desc &d = descs[i];
+        const uint64_t fb = wvb_frame_bytes(&d, out_format == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : out_format);
+        b->prepared_in_extent = std::max<uint64_t>(b->prepared_in_extent, d.in_offset + d.in_bytes);
+        b->prepared_out_extent = std::max<uint64_t>(b->prepared_out_extent, d.out_offset + (uint64_t)d.block_samples * fb);
+    }
     b->prepared = true;
     b->prepared_n = nblocks;
     b->prepared_fmt = out_format;
@@ -432,7 +443,8 @@ int wvb_batch_decode(wvb_batch *b, const uint8_t *in, size_t in_bytes, const wvb
     if (descs) {
         b->prepared = false;
         if ((rc = validate_table(descs, nblocks, in_bytes, out_bytes, out_format)) != WVB_OK) return rc;
-    }
+    } else if (b->prepared_in_extent > in_bytes || b->prepared_out_extent > out_bytes)
+        return set_error(WVB_E_ARG, "slabs smaller than the prepared table needs");
 
     if (descs && !(mem_flags & (WVB_IN_DEVICE | WVB_OUT_DEVICE | WVB_RESULTS_DEVICE))) {
         bool used = false;

@@ -91,14 +91,12 @@ struct BitReader {
     int bc;       // valid bits in bb
     uint32_t nw;  // word fetched one refill ahead: its load latency overlaps the decode of the bits before it
 
-    WVB_DEV uint32_t load_word() // bytes at or past `end` read as 0xFF; the slab is padded, so the aligned load itself is always legal
+    WVB_DEV uint32_t load_word() // bytes at or past `end` read as 0xFF (this three-way form measured faster than a single range test)
     {
-        uint32_t x = 0xFFFFFFFFu;
-        if (next < end) {
-            x = wvb_ld_u32(next);
-            const int rem = (int)(end - next);
-            if (rem < 4) x |= 0xFFFFFFFFu << (8 * rem);
-        }
+        uint32_t x;
+        if (next + 4 <= end) x = wvb_ld_u32(next);
+        else if (next >= end) x = 0xFFFFFFFFu;
+        else x = wvb_ld_u32(next) | (0xFFFFFFFFu << (8 * (int)(end - next)));
         next += 4;
         return x;
     }
