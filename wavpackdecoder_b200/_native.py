@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwvb.so")
+LIB_PATH = os.environ.get("WVB_LIB") or os.path.join(HERE, "libwvb.so")  # WVB_LIB: alternative build for tuning experiments
 
 WVB_SUB_COUNT = 8
 SUB_TERMS, SUB_WEIGHTS, SUB_SAMPLES, SUB_ENTROPY, SUB_HYBRID, SUB_WV, SUB_WVX, SUB_DSD = range(8)

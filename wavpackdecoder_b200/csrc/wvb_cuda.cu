@@ -22,7 +22,10 @@
 
 namespace {
 
-constexpr int CTA_THREADS = 128;
+#ifndef WVB_CTA
+#define WVB_CTA 128
+#endif
+constexpr int CTA_THREADS = WVB_CTA;
 
 thread_local std::string g_last_error;
 int set_error(int code, const std::string &msg)

@@ -27,6 +27,11 @@ static __device__ __forceinline__ uint8_t wvb_ld_u8(const uint8_t *p) { return _
 static __device__ __forceinline__ int wvb_ffs(uint32_t x) { return __ffs((int)x); }
 static __device__ __forceinline__ int wvb_clz(uint32_t x) { return __clz((int)x); }
 #define WVB_SYNCWARP() __syncwarp()
+#ifdef WVB_SYNC_LESS
+#define WVB_SYNCWARP_MID() ((void)0)
+#else
+#define WVB_SYNCWARP_MID() __syncwarp()
+#endif
 static __device__ __forceinline__ uint32_t wvb_warp_max(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
 #else
 #include <string.h>
@@ -38,6 +43,7 @@ static inline uint8_t wvb_ld_u8(const uint8_t *p) { return *p; }
 static inline int wvb_ffs(uint32_t x) { return x ? __builtin_ctz(x) + 1 : 0; }
 static inline int wvb_clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
 #define WVB_SYNCWARP() ((void)0)
+#define WVB_SYNCWARP_MID() ((void)0)
 static inline uint32_t wvb_warp_max(uint32_t v) { return v; }
 #endif
 
@@ -892,10 +898,10 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
         bool ok = act;
         if (!eof_fault) {
             if (ok) ok = decode_word<HYB, STEREO, 0>(br, w, flags, a);
-            WVB_SYNCWARP();
+            WVB_SYNCWARP_MID();
             if (STEREO) {
                 if (ok) ok = decode_word<HYB, STEREO, 1>(br, w, flags, b);
-                WVB_SYNCWARP();
+                WVB_SYNCWARP_MID();
             }
             if (act && !ok) { // get_words came back short (WordsUtils.cs:323,383,393): the reference still runs the passes and
                 eof_fault = true; // the CRC over the rest of the chunk, reading whatever the caller's buffer held.  We model
