@@ -464,7 +464,8 @@ template <bool STEREO> struct GenericDecorr {
 template <bool STEREO, int... TERMS> struct FixedDecorr {
     static constexpr bool kFixed = true;
     static constexpr int N = (int)sizeof...(TERMS);
-    int wA[N], wB[N], dl[N];
+    int wA[N], wB[N];
+    uint32_t dl; // the N 3-bit deltas packed (N <= 10)
     int hA[N][8], hB[N][8];
 
     static constexpr int term_at(int p)
@@ -478,6 +479,7 @@ template <bool STEREO, int... TERMS> struct FixedDecorr {
     template <class SMEM> WVB_DEV bool load(SMEM &SM, int nterms)
     {
         bool match = nterms == N;
+        dl = 0;
 #pragma unroll
         for (int p = 0; p < N; ++p) {
             constexpr int T[N] = {TERMS...};
@@ -485,7 +487,7 @@ template <bool STEREO, int... TERMS> struct FixedDecorr {
             const uint32_t d = match ? (uint32_t)SM(p) : 0u;
             if ((int)(d & 31u) - 5 != term) match = false;
             const int mask = (int)((d >> 8) & 7u), base = (int)(d >> 16);
-            dl[p] = (int)((d >> 5) & 7u);
+            dl |= ((d >> 5) & 7u) << (3 * p);
             wA[p] = match ? SM(base) : 0;
             wB[p] = (STEREO && match) ? SM(base + 1) : 0;
             const int hb = base + (STEREO ? 2 : 1);
@@ -525,7 +527,7 @@ template <bool STEREO, int... TERMS> struct FixedDecorr {
     {
         constexpr int T[N] = {TERMS...};
         constexpr int term = T[P];
-        const int delta = dl[P];
+        const int delta = (int)((dl >> (3 * P)) & 7u);
         if (term > 0) {
             int s = predict<term>(hA[P]);
             const int oa = a + apply_weight(wA[P], s);
@@ -688,6 +690,24 @@ WVB_DEV void store_unit(uint8_t *q, int v, int unit, int add128)
     else if (unit == 2) *(uint16_t *)q = (uint16_t)v;
     else if (unit == 3) { q[0] = (uint8_t)v; q[1] = (uint8_t)(v >> 8); q[2] = (uint8_t)(v >> 16); }
     else q[0] = (uint8_t)(v + add128);
+}
+
+// The reference decodes a block in caller-sized pieces (one unpack_samples call each).  piece_bounds() recovers the piece
+// [ps, pe) that contains sample t from the descriptor's chunk grid; it is evaluated only at piece events and on faults, so
+// the grid costs one register (the next event) in the sample loop.
+WVB_DEV void piece_bounds(const wvb_block_desc &D, uint32_t n, uint32_t t, uint32_t &ps, uint32_t &pe)
+{
+    const uint32_t chunk = D.chunk_samples ? D.chunk_samples : 0xffffffffu;
+    uint32_t first = D.chunk_first < n ? D.chunk_first : n;
+    if (first == 0) first = chunk < n ? chunk : n;
+    if (t < first) { ps = 0; pe = first; return; }
+    ps = first + ((t - first) / chunk) * chunk;
+    pe = (n - ps) < chunk ? n : ps + chunk;
+}
+// next sample index at which the weights are cast to short: 8 samples into a stereo piece of >= 16 samples, and the piece end
+template <bool STEREO> WVB_DEV uint32_t next_piece_event(uint32_t t, uint32_t ps, uint32_t pe)
+{
+    return (STEREO && pe - ps >= 16 && t < ps + 8) ? ps + 8 : pe;
 }
 
 // ---- the per-thread block decoder ------------------------------------------------------------
@@ -868,31 +888,29 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
     const bool joint = STEREO && (flags & F_JOINT);
     const int fast16 = (!GENFIX && STEREO && out_format == WVB_OUT_PCM && unit == 2 && D.out_stride == 2 && D.out_ch_offset == 0) ? 1 : 0;
 
-    // call/chunk grid (weights are cast to short at the end of every pass call: after the first 8 samples of a
-    // stereo piece of >= 16 samples and at the end of the piece)
-    const uint32_t chunk = D.chunk_samples ? D.chunk_samples : 0xffffffffu;
-    uint32_t piece_start = 0;
-    uint32_t piece_end = D.chunk_first < n ? D.chunk_first : n;
-    if (piece_end == 0) piece_end = chunk < n ? chunk : n;
-    uint32_t trunc8 = (STEREO && piece_end - piece_start >= 16) ? piece_start + 8 : 0xffffffffu;
+    // call/chunk grid: weights are cast to short at the end of every pass call, i.e. after the first 8 samples of a stereo
+    // piece of >= 16 samples and at the end of the piece (UnpackUtils.cs:604-605,942-943,1152-1153,1239)
+    uint32_t next_ev;
+    {
+        uint32_t ps, pe;
+        piece_bounds(D, n, 0, ps, pe);
+        next_ev = next_piece_event<STEREO>(0, ps, pe);
+    }
 
     int crc = -1;
     bool fault = false, eof_fault = false;
+    uint32_t fault_t = 0;
     // All 32 lanes of a warp iterate together (warp-max trip count) and re-join at the top of every sample:
     // a lane left behind by a divergent branch must not be allowed to run the rest of its block alone.
     const uint32_t nmax = wvb_warp_max(n);
     for (uint32_t t = 0; t < nmax; ++t) {
         WVB_SYNCWARP();
         const bool act = t < n && !fault;
-        if (act) {
-            if (t == piece_end) {
-                dec.truncate(SM, nterms);
-                piece_start = t;
-                const uint32_t rest = n - t;
-                piece_end = t + (chunk < rest ? chunk : rest);
-                trunc8 = (STEREO && piece_end - piece_start >= 16) ? piece_start + 8 : 0xffffffffu;
-            } else if (t == trunc8)
-                dec.truncate(SM, nterms);
+        if (act && t == next_ev) {
+            dec.truncate(SM, nterms);
+            uint32_t ps, pe;
+            piece_bounds(D, n, t, ps, pe);
+            next_ev = next_piece_event<STEREO>(t, ps, pe);
         }
         int a = 0, b = 0;
         bool ok = act;
@@ -936,11 +954,19 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
             }
             op += frame_bytes;
         }
-        if (act && (!ok || (eof_fault && t + 1 == piece_end))) fault = true;
+        if (act && !ok) fault = true;
+        if (act && eof_fault && !fault) { // the modelled remainder of the chunk ends with the piece
+            uint32_t ps, pe;
+            piece_bounds(D, n, t, ps, pe);
+            if (t + 1 == pe) fault = true;
+        }
+        if (fault && act) fault_t = t;
     }
 
     if (fault) { // mute from the start of the caller chunk that contains the fault (UnpackUtils.cs:649-664, App. E-10)
         rflags |= WVB_RF_MUTED;
+        uint32_t piece_start, piece_end;
+        piece_bounds(D, n, fault_t, piece_start, piece_end);
         uint8_t *q = out + D.out_offset + (uint32_t)unit * D.out_ch_offset + (uint64_t)piece_start * frame_bytes;
         // the first muted chunk still runs through fixup_samples with zeros; only INT32 "ones" (and WVX data bits) make that non-zero
         for (uint32_t i = piece_start; i < n; ++i, q += frame_bytes) {
