@@ -143,7 +143,6 @@ void wvenc_synth(const wvenc_config *cfg, uint64_t seed, int64_t nsamples, int32
     int nch = cfg->channels;
     if (cfg->kind == WVENC_DSD) {
         /* 2nd-order sigma-delta of a 16-bit synthetic signal, 8 one-bit samples per output byte, MSB first */
-        i64 nbits = nsamples * 8;
         i32 *pcm = (i32 *)malloc(sizeof(i32) * (size_t)(nsamples + 1) * nch);
         wvenc_config c2 = *cfg;
         c2.kind = WVENC_PCM;
@@ -162,7 +161,6 @@ void wvenc_synth(const wvenc_config *cfg, uint64_t seed, int64_t nsamples, int32
                 out[t * nch + c] = (i32)byte;
             }
         }
-        (void)nbits;
         free(pcm);
         return;
     }
@@ -720,11 +718,9 @@ static void encode_pcm_block(encoder *E, stream_state *S, const i32 *srcL, const
     }
     /* history: stored through 16-bit logs; only the encoder-first pass (decoder's last) unless ALL_HISTORY */
     int16_t hlog[16][2][8];
-    int hcount[16];
     for (int d = 0; d < nt; d++) {
         int keep = (d == nt - 1) || (cfg->extras & WVENC_X_ALL_HISTORY);
         int cnt = P[d].term > 8 ? 2 : (P[d].term < 0 ? 1 : P[d].term);
-        hcount[d] = cnt;
         for (int j = 0; j < 8; j++) {
             if (!keep || j >= cnt) { P[d].hA[j] = 0; P[d].hB[j] = 0; if (j < 8) { hlog[d][0][j] = hlog[d][1][j] = 0; } continue; }
             hlog[d][0][j] = (int16_t)log2s(P[d].hA[j]); P[d].hA[j] = exp2s(hlog[d][0][j]);
@@ -907,7 +903,6 @@ static void encode_pcm_block(encoder *E, stream_state *S, const i32 *srcL, const
                     if (stereo) { tmp[k++] = (uint8_t)hlog[d][1][j]; tmp[k++] = (uint8_t)(hlog[d][1][j] >> 8); }
                 }
             }
-            (void)hcount;
         }
         put_meta(o, 0x04, tmp, (size_t)k);
     }
@@ -952,7 +947,6 @@ static void encode_pcm_block(encoder *E, stream_state *S, const i32 *srcL, const
     if (has_wvx || cfg->kind == WVENC_FLOAT) {
         size_t xl = bw_close(&xw);
         /* sub-block = 4-byte crc + payload, even length, > 4 bytes */
-        size_t at = o->len;
         size_t plen = 4 + xl;
         if (plen < 6) plen = 6;
         if (plen & 1) plen++;
@@ -963,7 +957,6 @@ static void encode_pcm_block(encoder *E, stream_state *S, const i32 *srcL, const
         int newfmt = cfg->kind == WVENC_FLOAT ? cfg->float_new_wvx : cfg->int32_new_wvx;
         put_meta(o, newfmt ? 0x2c : 0x0c, blob, plen);
         free(blob);
-        (void)at;
     }
     if (cfg->extras & WVENC_X_BLOCK_CHECKSUM) { tmp[0] = 0x12; tmp[1] = 0x34; put_meta(o, 0x2f, tmp, 2); }
     if (!o->overflow) {

@@ -44,7 +44,6 @@ struct Ctx { // the parts of WavpackContext/WavpackStream the index pass must ca
     size_t len;
     size_t pos = 0; // infile position
     Header hdr;
-    bool hdr_valid = false;
     wvb_file_info *info;
     // persistent stream state (quirk C-8)
     int num_terms = 0;
@@ -90,7 +89,6 @@ bool read_next_header(Ctx &c)
             h.crc = (int32_t)le32(b + 28);
             h.pos = p;
             c.pos = p + 32;
-            c.hdr_valid = true;
             return true;
         }
         size_t q = p + 1;
