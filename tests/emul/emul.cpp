@@ -65,7 +65,8 @@ extern "C" int emul_decode(const uint8_t *in, const wvb_block_desc *descs, size_
                 uint32_t fail_at = total;
                 wvb::dsd_fast_decode(T, bins, p, len, at, mono, total,
                     [](const uint16_t *row, uint32_t index) { int c = 0; for (int k = 0; k < 256; k++) c += row[k] <= index; return c; },
-                    [&](uint32_t j, int code) { o.put(j, code); }, crc, failed, fail_at);
+                    [&](int p0, uint32_t nn) { return nn / summed[(size_t)p0 * 256 + 255]; },
+                    [&](uint32_t j, int code) { o.put(j, code); }, [](uint32_t) {}, crc, failed, fail_at);
                 wvb::dsd_finish(D, &r, crc, failed, mono ? fail_at : fail_at >> 1, 0);
             } else
                 r.rflags = WVB_RF_BAD_BLOCK;

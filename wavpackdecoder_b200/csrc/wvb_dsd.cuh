@@ -135,6 +135,14 @@ k_dsd_fast(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ de
     int crc = -1;
     bool failed = false;
     uint32_t fail_at = total;
+    // per-bin reciprocal of summed[bin][255] (16-bit divisor d, 32-bit numerator n): with m = ceil(2^48 / d),
+    // n / d == (n * m) >> 48 exactly (m*d - 2^48 < d <= 2^16, Granlund-Montgomery).  Lane b owns bin b.
+    uint64_t my_recip = 0;
+    if (lane < bins) {
+        const uint32_t d = T.summed[lane * 256 + 255];
+        my_recip = d ? (((uint64_t)1 << 48) + d - 1) / d : 0;
+    }
+    int mine = 0; // the value this lane will store at the next flush (lane == j & 31)
     dsd_fast_decode(T, bins, p, len, at, mono, total,
         [&](const uint16_t *row, uint32_t index) {
             const uint4 v = *(const uint4 *)(row + lane * 8);
@@ -142,7 +150,17 @@ k_dsd_fast(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ de
             const int c = (__popc(__vcmpleu2(v.x, idx2)) + __popc(__vcmpleu2(v.y, idx2)) + __popc(__vcmpleu2(v.z, idx2)) + __popc(__vcmpleu2(v.w, idx2))) >> 4;
             return (int)__reduce_add_sync(0xffffffffu, (unsigned)c);
         },
-        [&](uint32_t j, int code) { if ((int)(j & 31u) == lane) o.put(j, code); },
+        [&](int p0, uint32_t n) {
+            const uint64_t m = __shfl_sync(0xffffffffu, my_recip, p0);
+            return (uint32_t)__umul64hi((uint64_t)n << 16, m);
+        },
+        [&](uint32_t j, int code) {
+            if ((int)(j & 31u) == lane) mine = code;
+            if ((j & 31u) == 31u) o.put((j & ~31u) + (uint32_t)lane, mine); // one coalesced store per 32 values
+        },
+        [&](uint32_t count) { // values of the last, partial group
+            if ((count & 31u) != 0 && (uint32_t)lane < (count & 31u)) o.put((count & ~31u) + (uint32_t)lane, mine);
+        },
         crc, failed, fail_at);
     if (lane == 0) dsd_finish(D, &results[bi], crc, failed, mono ? fail_at : fail_at >> 1, 0);
 }

@@ -291,9 +291,11 @@ template <class SCAN> WVB_DEV void dsd_fast_sums(const DsdFastTables &T, int bin
 }
 
 // FIND(row, index) -> number of entries of row[0..255] that are <= index (== the decoded symbol)
-template <class FIND, class EMIT>
+// DIVSUM(p0, n)    -> n / summed[p0][255] (the device uses a per-bin reciprocal, the divisor only changes with the bin)
+// EMIT(j, code)    -> deliver the j-th decoded value;  DONE(count) is called once with the number of values delivered
+template <class FIND, class DIVSUM, class EMIT, class DONE>
 WVB_DEV void dsd_fast_decode(const DsdFastTables &T, int bins, const uint8_t *p, uint32_t len, uint32_t at, bool mono, uint32_t total,
-                             FIND find, EMIT emit, int &crc_out, bool &failed, uint32_t &fail_at)
+                             FIND find, DIVSUM divsum, EMIT emit, DONE done, int &crc_out, bool &failed, uint32_t &fail_at)
 {
     RangeDec rc;
     rc.br.init(p, len, at);
@@ -304,11 +306,12 @@ WVB_DEV void dsd_fast_decode(const DsdFastTables &T, int bins, const uint8_t *p,
     int p0 = 0, p1 = 0, crc = -1;
     failed = false;
     fail_at = total;
-    for (uint32_t j = 0; j < total; ++j) { // DsdUtils.cs:251-301
+    uint32_t j = 0;
+    for (; j < total; ++j) { // DsdUtils.cs:251-301
         const uint16_t *row = T.summed + p0 * 256;
         const uint32_t sum = row[255];
         if (sum == 0) { failed = true; fail_at = j; break; }
-        uint32_t mult = (rc.high - rc.low) / sum;
+        uint32_t mult = divsum(p0, rc.high - rc.low);
         if (mult == 0) {
             if (rc.br.left() >= 4)
                 for (int i = 0; i < 4; ++i) rc.value = (rc.value << 8) | rc.br.get();
@@ -329,6 +332,7 @@ WVB_DEV void dsd_fast_decode(const DsdFastTables &T, int bins, const uint8_t *p,
         else { p0 = p1; p1 = code & (bins - 1); }
         rc.normalize();
     }
+    done(j);
     crc_out = crc;
 }
 
