@@ -64,8 +64,14 @@ extern "C" int emul_decode(const uint8_t *in, const wvb_block_desc *descs, size_
                 bool failed = false;
                 uint32_t fail_at = total;
                 wvb::dsd_fast_decode(T, bins, p, len, at, mono, total,
-                    [](const uint16_t *row, uint32_t index) { int c = 0; for (int k = 0; k < 256; k++) c += row[k] <= index; return c; },
-                    [&](int p0, uint32_t nn) { return nn / summed[(size_t)p0 * 256 + 255]; },
+                    [](const uint16_t *row, int) { return (uint32_t)row[255]; },
+                    [](const uint16_t *row, int, uint32_t index, uint32_t &below, uint32_t &cur) {
+                        int c = 0;
+                        for (int k = 0; k < 256; k++) c += row[k] <= index;
+                        below = c > 0 ? row[c - 1] : 0u;
+                        cur = row[c];
+                        return c;
+                    },
                     [&](uint32_t j, int code) { o.put(j, code); }, [](uint32_t) {}, crc, failed, fail_at);
                 wvb::dsd_finish(D, &r, crc, failed, mono ? fail_at : fail_at >> 1, 0);
             } else

@@ -75,6 +75,8 @@ struct wvb_batch {
     wvb_block_desc *d_descs = nullptr; size_t d_descs_cap = 0;
     uint32_t *d_order = nullptr; size_t d_order_cap = 0;
     wvb_block_result *d_results = nullptr; size_t d_results_cap = 0;
+    uint8_t *d_scratch = nullptr; size_t d_scratch_cap = 0;       // DSD fast-mode tables, one 16 KB slot per table position
+    uint8_t *d_scratch_meta = nullptr; size_t d_scratch_meta_cap = 0;
     std::vector<uint32_t> order;
     std::vector<Launch> plan;
     size_t prepared_n = 0; bool prepared = false; int prepared_fmt = -1;
@@ -211,6 +213,7 @@ void wvb_batch_destroy(wvb_batch *b)
     cudaSetDevice(b->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
     cudaFree(b->d_in); cudaFree(b->d_out); cudaFree(b->d_descs); cudaFree(b->d_order); cudaFree(b->d_results);
+    cudaFree(b->d_scratch); cudaFree(b->d_scratch_meta);
     for (auto &e : b->ev) if (e) cudaEventDestroy(e);
     for (auto &e : b->seg_ev) if (e) cudaEventDestroy(e);
     for (auto &st : b->seg_streams) if (st) cudaStreamDestroy(st);
@@ -273,13 +276,31 @@ static int upload_table(wvb_batch *b, const wvb_block_desc *descs, size_t nblock
     return WVB_OK;
 }
 
+// DSD fast-mode tables live in a scratch buffer sized once per table, BEFORE any launch (growing it later would free memory
+// that kernels of an earlier segment still use)
+static int ensure_dsd_scratch(wvb_batch *b, const std::vector<Launch> &plan)
+{
+    size_t slots = 0;
+    for (const Launch &L : plan)
+        if (L.variant == wvb::V_DSD && L.cls >= 16) slots = std::max(slots, (size_t)L.first + L.count);
+    if (!slots) return WVB_OK;
+    int rc;
+    if (slots * wvb::DSD_FAST_TABLE_STRIDE > b->d_scratch_cap || slots * sizeof(wvb::DsdFastMeta) > b->d_scratch_meta_cap)
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+    if ((rc = ensure(b->d_scratch, b->d_scratch_cap, slots * wvb::DSD_FAST_TABLE_STRIDE)) != WVB_OK) return rc;
+    return ensure(b->d_scratch_meta, b->d_scratch_meta_cap, slots * sizeof(wvb::DsdFastMeta));
+}
+
 static int launch_plan(wvb_batch *b, const std::vector<Launch> &plan, const uint8_t *din, uint8_t *dout, int fmt, wvb_block_result *dres, cudaStream_t s)
 {
     int rc;
     for (const Launch &L : plan) {
         if (L.variant == wvb::V_DSD) {
+            // fast mode: scratch slots are indexed by position in the order array, so concurrent launches never share one
+            if (L.cls >= 16 && ((size_t)L.first + L.count) * wvb::DSD_FAST_TABLE_STRIDE > b->d_scratch_cap)
+                return set_error(WVB_E_ARG, "internal: DSD scratch not sized before launch");
             if ((rc = wvb::launch_dsd(L.cls, din, b->d_descs, b->d_order + L.first, L.count, dout, fmt, dres, s, b->smem_optin, b->device,
-                                      &b->launches)) != WVB_OK)
+                                      &b->launches, b->d_scratch, b->d_scratch_meta, L.first)) != WVB_OK)
                 return set_error(rc, std::string("DSD launch failed (unsupported dsd mode or CUDA error): ") + cudaGetErrorString(cudaGetLastError()));
             continue;
         }
@@ -372,6 +393,8 @@ static int decode_pipelined(wvb_batch *b, const uint8_t *in, size_t in_bytes, co
     }
     b->plan.clear();
     b->prepared = false;
+    for (const auto &pl : plans)
+        if ((rc = ensure_dsd_scratch(b, pl)) != WVB_OK) return rc;
     CUDA_TRY(cudaEventRecord(b->ev[0], s));
     CUDA_TRY(cudaMemcpyAsync(b->d_descs, descs, nblocks * sizeof(wvb_block_desc), cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(b->d_order, b->order.data(), nblocks * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
@@ -478,6 +501,7 @@ int wvb_batch_decode(wvb_batch *b, const uint8_t *in, size_t in_bytes, const wvb
     if (descs && (rc = upload_table(b, descs, nblocks)) != WVB_OK) return rc;
     CUDA_TRY(cudaEventRecord(b->ev[1], s));
 
+    if ((rc = ensure_dsd_scratch(b, b->plan)) != WVB_OK) return rc;
     if ((rc = launch_plan(b, b->plan, din, dout, out_format, dres, s)) != WVB_OK) return rc;
     CUDA_TRY(cudaEventRecord(b->ev[2], s));
 

@@ -97,72 +97,129 @@ k_dsd_high(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ de
     dsd_decode_high(PT, ptables + 256 * dsd_key_rate(D.smem_words), in, D, out, out_format, &results[bi], valid);
 }
 
+// ---- mode 1 ("fast"), two kernels -------------------------------------------------------------
+// (1) k_dsd_fast_build, one block per warp: RLE-decode the probability tables and prefix-sum them into a global scratch
+//     table (bins x 256 u16 cumulative sums, 512 B per history bin).
+// (2) k_dsd_fast_dec, one block per THREAD: the range decoder.  A warp-per-block decoder spends ~130 warp instructions per
+//     symbol on uniform work (ncu: issue-bound at 73%, profiles/r01_ncu_dsd_fast_warp_per_block.txt); per thread the same
+//     work advances 32 blocks.  Each thread keeps a 16-entry coarse index per bin (every 16th cumulative sum) in shared
+//     memory [word][thread]; the symbol lookup is a coarse count there plus a fine count over one 32-byte sector of its
+//     global table.
+constexpr int DSD_FAST_DEC_THREADS = 128;
+constexpr size_t DSD_FAST_TABLE_STRIDE = 32 * 512; // scratch bytes per block (room for 32 bins)
+
+struct DsdFastMeta { uint32_t at; uint32_t bins; }; // payload offset after the tables (0 = rejected), history bins
+
 static __global__ void __launch_bounds__(DSD_FAST_WARPS * 32)
-k_dsd_fast(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ descs, const uint32_t *__restrict__ order, uint32_t count,
-           uint8_t *__restrict__ out, int out_format, wvb_block_result *__restrict__ results, int bins_max)
+k_dsd_fast_build(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ descs, const uint32_t *__restrict__ order, uint32_t count,
+                 uint8_t *__restrict__ scratch, DsdFastMeta *__restrict__ meta)
 {
-    extern __shared__ int dsd_smem[];
     const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
     const uint32_t w = blockIdx.x * DSD_FAST_WARPS + wic;
     if (w >= count) return; // whole warp leaves together
-    const uint32_t bi = order[w];
-    const wvb_block_desc &D = descs[bi];
+    const wvb_block_desc &D = descs[order[w]];
     DsdFastTables T;
-    T.summed = (uint16_t *)((uint8_t *)dsd_smem + (size_t)wic * bins_max * 512);
+    T.summed = (uint16_t *)(scratch + (size_t)w * DSD_FAST_TABLE_STRIDE);
     const uint8_t *p = in + D.in_offset + D.sub_off[WVB_SUB_DSD];
-    const uint32_t len = D.sub_len[WVB_SUB_DSD];
     int bins = 1;
-    const uint32_t at = dsd_fast_build(T, p, len, lane, 32, bins);
+    const uint32_t at = dsd_fast_build(T, p, D.sub_len[WVB_SUB_DSD], lane, 32, bins);
     __syncwarp();
-    if (at == 0 || bins > bins_max) {
-        if (lane == 0) { results[bi].crc = -1; results[bi].crc_x = -1; results[bi].mute_from = 0; results[bi].rflags = WVB_RF_BAD_BLOCK | WVB_RF_MUTED | WVB_RF_CRC_ERROR; }
-        return;
-    }
-    dsd_fast_sums(T, bins, lane, 32, [&](uint32_t local) {
-        uint32_t incl = local;
+    if (at != 0) {
+        dsd_fast_sums(T, bins, lane, 32, [&](uint32_t local) {
+            uint32_t incl = local;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += v;
-        }
-        return incl - local;
-    });
-    __syncwarp();
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            return incl - local;
+        });
+    }
+    if (lane == 0) { meta[w].at = at; meta[w].bins = (uint32_t)bins; }
+}
+
+struct CoarseColumn { // word i of this thread's coarse index: [word][DSD_FAST_DEC_THREADS]
+    uint32_t *base;
+    __device__ __forceinline__ uint32_t &operator()(int i) { return base[i * DSD_FAST_DEC_THREADS]; }
+};
+
+static __global__ void __launch_bounds__(DSD_FAST_DEC_THREADS)
+k_dsd_fast_dec(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ descs, const uint32_t *__restrict__ order, uint32_t count,
+               uint8_t *__restrict__ out, int out_format, wvb_block_result *__restrict__ results, const uint8_t *__restrict__ scratch,
+               const DsdFastMeta *__restrict__ meta)
+{
+    extern __shared__ int dsd_smem[];
+    const uint32_t i = blockIdx.x * DSD_FAST_DEC_THREADS + threadIdx.x;
+    const bool valid = i < count; // lanes past the end stay in the warp with no work (warp-synchronous loop)
+    const uint32_t slot = valid ? i : count - 1;
+    const uint32_t bi = order[slot];
+    const wvb_block_desc &D = descs[bi];
+    const DsdFastMeta M = meta[slot];
+    const bool good = valid && M.at != 0;
+    const int bins = good ? (int)M.bins : 1;
+    DsdFastTables T;
+    T.summed = (uint16_t *)(scratch + (size_t)slot * DSD_FAST_TABLE_STRIDE);
+    CoarseColumn CO{(uint32_t *)dsd_smem + threadIdx.x};
+    if (good)
+        for (int b = 0; b < bins; ++b)
+            for (int k = 0; k < 8; ++k) // entries 16*(2k)+15 and 16*(2k+1)+15 of bin b
+                CO(b * 8 + k) = (uint32_t)T.summed[b * 256 + 32 * k + 15] | ((uint32_t)T.summed[b * 256 + 32 * k + 31] << 16);
     DsdOut o;
     dsd_out_init(o, D, out, out_format);
     const bool mono = o.coded_ch == 1;
-    const uint32_t total = D.block_samples * (uint32_t)o.coded_ch;
+    const uint32_t total = good ? D.block_samples * (uint32_t)o.coded_ch : 0;
+    const bool packed = o.unit == 1 && o.frame_bytes == (uint32_t)o.coded_ch && o.out_ch == o.coded_ch && (((uintptr_t)o.op) & 3) == 0;
+    const uint32_t addv = (uint32_t)o.add;
+    uint32_t acc = 0;
     int crc = -1;
     bool failed = false;
     uint32_t fail_at = total;
-    // per-bin reciprocal of summed[bin][255] (16-bit divisor d, 32-bit numerator n): with m = ceil(2^48 / d),
-    // n / d == (n * m) >> 48 exactly (m*d - 2^48 < d <= 2^16, Granlund-Montgomery).  Lane b owns bin b.
-    uint64_t my_recip = 0;
-    if (lane < bins) {
-        const uint32_t d = T.summed[lane * 256 + 255];
-        my_recip = d ? (((uint64_t)1 << 48) + d - 1) / d : 0;
-    }
-    int mine = 0; // the value this lane will store at the next flush (lane == j & 31)
-    dsd_fast_decode(T, bins, p, len, at, mono, total,
-        [&](const uint16_t *row, uint32_t index) {
-            const uint4 v = *(const uint4 *)(row + lane * 8);
+    const uint8_t *p = in + D.in_offset + D.sub_off[WVB_SUB_DSD];
+    dsd_fast_decode(T, bins, p, D.sub_len[WVB_SUB_DSD], good ? M.at : 6u, mono, total,
+        [&](const uint16_t *, int p0) { return CO(p0 * 8 + 7) >> 16; }, // row[255] is the last coarse entry
+        [&](const uint16_t *row, int p0, uint32_t index, uint32_t &below, uint32_t &cur) {
             const uint32_t idx2 = index | (index << 16);
-            const int c = (__popc(__vcmpleu2(v.x, idx2)) + __popc(__vcmpleu2(v.y, idx2)) + __popc(__vcmpleu2(v.z, idx2)) + __popc(__vcmpleu2(v.w, idx2))) >> 4;
-            return (int)__reduce_add_sync(0xffffffffu, (unsigned)c);
-        },
-        [&](int p0, uint32_t n) {
-            const uint64_t m = __shfl_sync(0xffffffffu, my_recip, p0);
-            return (uint32_t)__umul64hi((uint64_t)n << 16, m);
+            int c = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) c += __popc(__vcmpleu2(CO(p0 * 8 + k), idx2));
+            c >>= 4; // coarse cell 0..15 (index < row[255] keeps it below 16)
+            const uint4 *q = (const uint4 *)(row + 16 * c);
+            const uint4 a = q[0], b = q[1]; // the cell: 16 cumulative sums = one 32-byte sector of this block's table
+            const int f = (__popc(__vcmpleu2(a.x, idx2)) + __popc(__vcmpleu2(a.y, idx2)) + __popc(__vcmpleu2(a.z, idx2)) + __popc(__vcmpleu2(a.w, idx2)) +
+                           __popc(__vcmpleu2(b.x, idx2)) + __popc(__vcmpleu2(b.y, idx2)) + __popc(__vcmpleu2(b.z, idx2)) + __popc(__vcmpleu2(b.w, idx2))) >> 4;
+            // row[16c+f] and row[16c+f-1] straight out of the registers (no second trip to memory)
+            auto entry = [&](int e) { // e in 0..15
+                const bool hi = e >= 8;
+                const uint32_t w0 = hi ? b.x : a.x, w1 = hi ? b.y : a.y, w2 = hi ? b.z : a.z, w3 = hi ? b.w : a.w;
+                const int k = (e >> 1) & 3;
+                const uint32_t w = k == 0 ? w0 : k == 1 ? w1 : k == 2 ? w2 : w3;
+                return (e & 1) ? (w >> 16) : (w & 0xffffu);
+            };
+            cur = entry(f);
+            if (f > 0) below = entry(f - 1);
+            else if (c > 0) { // last entry of the previous cell = coarse entry c-1
+                const uint32_t cw = CO(p0 * 8 + ((c - 1) >> 1));
+                below = ((c - 1) & 1) ? (cw >> 16) : (cw & 0xffffu);
+            } else
+                below = 0;
+            return 16 * c + f;
         },
         [&](uint32_t j, int code) {
-            if ((int)(j & 31u) == lane) mine = code;
-            if ((j & 31u) == 31u) o.put((j & ~31u) + (uint32_t)lane, mine); // one coalesced store per 32 values
+            if (packed) { // four byte values per 32-bit store
+                acc |= (((uint32_t)code + addv) & 0xffu) << (8 * (j & 3u));
+                if ((j & 3u) == 3u) { *(uint32_t *)(o.op + (j & ~3u)) = acc; acc = 0; }
+            } else
+                o.put(j, code);
         },
-        [&](uint32_t count) { // values of the last, partial group
-            if ((count & 31u) != 0 && (uint32_t)lane < (count & 31u)) o.put((count & ~31u) + (uint32_t)lane, mine);
+        [&](uint32_t delivered) {
+            if (packed)
+                for (uint32_t k = delivered & ~3u; k < delivered; ++k) o.op[k] = (uint8_t)(acc >> (8 * (k & 3u)));
         },
         crc, failed, fail_at);
-    if (lane == 0) dsd_finish(D, &results[bi], crc, failed, mono ? fail_at : fail_at >> 1, 0);
+    if (valid) {
+        if (!good) { results[bi].crc = -1; results[bi].crc_x = -1; results[bi].mute_from = 0; results[bi].rflags = WVB_RF_BAD_BLOCK | WVB_RF_MUTED | WVB_RF_CRC_ERROR; }
+        else dsd_finish(D, &results[bi], crc, failed, mono ? fail_at : fail_at >> 1, 0);
+    }
 }
 
 // second pass over the DSD blocks of a launch: 0x55 fill for muted pieces (DsdUtils.cs:104-117), after every decode
@@ -218,7 +275,8 @@ inline const int *dsd_device_ptables(int device)
 
 // returns WVB_OK or an error code; the caller reports cudaGetLastError text
 inline int launch_dsd(int cls, const uint8_t *din, const wvb_block_desc *d_descs, const uint32_t *d_order, uint32_t count, uint8_t *dout,
-                      int out_format, wvb_block_result *dres, cudaStream_t s, size_t smem_optin, int device, int *launches)
+                      int out_format, wvb_block_result *dres, cudaStream_t s, size_t smem_optin, int device, int *launches,
+                      uint8_t *scratch, uint8_t *scratch_meta, uint32_t scratch_slot0)
 {
     if (count == 0) return WVB_OK;
     if (cls == 0) {
@@ -231,11 +289,18 @@ inline int launch_dsd(int cls, const uint8_t *din, const wvb_block_desc *d_descs
         if (cudaFuncSetAttribute((const void *)k_dsd_high, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WVB_E_CUDA;
         k_dsd_high<<<(count + DSD_HIGH_THREADS - 1) / DSD_HIGH_THREADS, DSD_HIGH_THREADS, smem, s>>>(din, d_descs, d_order, count, dout, out_format, dres, pt);
     } else if (cls >= 16 && cls <= 16 + 5) {
+        if (!scratch) return WVB_E_ARG;
         const int bins = 1 << (cls - 16);
-        const size_t smem = (size_t)DSD_FAST_WARPS * bins * 512;
+        uint8_t *tab = scratch + (size_t)scratch_slot0 * DSD_FAST_TABLE_STRIDE;
+        DsdFastMeta *meta = (DsdFastMeta *)(scratch_meta) + scratch_slot0;
+        k_dsd_fast_build<<<(count + DSD_FAST_WARPS - 1) / DSD_FAST_WARPS, DSD_FAST_WARPS * 32, 0, s>>>(din, d_descs, d_order, count, tab, meta);
+        if (cudaGetLastError() != cudaSuccess) return WVB_E_CUDA;
+        if (launches) (*launches)++;
+        const size_t smem = (size_t)bins * 8 * sizeof(uint32_t) * DSD_FAST_DEC_THREADS;
         if (smem > smem_optin) return WVB_E_ARG;
-        if (cudaFuncSetAttribute((const void *)k_dsd_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WVB_E_CUDA;
-        k_dsd_fast<<<(count + DSD_FAST_WARPS - 1) / DSD_FAST_WARPS, DSD_FAST_WARPS * 32, smem, s>>>(din, d_descs, d_order, count, dout, out_format, dres, bins);
+        if (cudaFuncSetAttribute((const void *)k_dsd_fast_dec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WVB_E_CUDA;
+        k_dsd_fast_dec<<<(count + DSD_FAST_DEC_THREADS - 1) / DSD_FAST_DEC_THREADS, DSD_FAST_DEC_THREADS, smem, s>>>(din, d_descs, d_order, count, dout,
+                                                                                                           out_format, dres, tab, meta);
     } else
         return WVB_E_ARG;
     if (cudaGetLastError() != cudaSuccess) return WVB_E_CUDA;

@@ -290,12 +290,15 @@ template <class SCAN> WVB_DEV void dsd_fast_sums(const DsdFastTables &T, int bin
     }
 }
 
-// FIND(row, index) -> number of entries of row[0..255] that are <= index (== the decoded symbol)
-// DIVSUM(p0, n)    -> n / summed[p0][255] (the device uses a per-bin reciprocal, the divisor only changes with the bin)
-// EMIT(j, code)    -> deliver the j-th decoded value;  DONE(count) is called once with the number of values delivered
-template <class FIND, class DIVSUM, class EMIT, class DONE>
+// The symbol loop of decode_fast (DsdUtils.cs:251-301) for ONE block per thread.  32 lanes run it in lock step on 32
+// different blocks (warp-max trip count, __syncwarp per symbol, single exit), like the PCM sample loop.
+// SUMOF(row, p0)       -> row[255], the total of history bin p0 (the device keeps it on chip)
+// FIND(row, p0, index, below, cur) -> the decoded symbol = number of entries of row[0..255] that are <= index; also returns
+//                         below = row[symbol-1] (0 for symbol 0) and cur = row[symbol]
+// EMIT(j, code)        -> deliver the j-th decoded value;  DONE(count) is called once with the number of values delivered
+template <class SUMOF, class FIND, class EMIT, class DONE>
 WVB_DEV void dsd_fast_decode(const DsdFastTables &T, int bins, const uint8_t *p, uint32_t len, uint32_t at, bool mono, uint32_t total,
-                             FIND find, DIVSUM divsum, EMIT emit, DONE done, int &crc_out, bool &failed, uint32_t &fail_at)
+                             SUMOF sumof, FIND find, EMIT emit, DONE done, int &crc_out, bool &failed, uint32_t &fail_at)
 {
     RangeDec rc;
     rc.br.init(p, len, at);
@@ -306,33 +309,48 @@ WVB_DEV void dsd_fast_decode(const DsdFastTables &T, int bins, const uint8_t *p,
     int p0 = 0, p1 = 0, crc = -1;
     failed = false;
     fail_at = total;
-    uint32_t j = 0;
-    for (; j < total; ++j) { // DsdUtils.cs:251-301
-        const uint16_t *row = T.summed + p0 * 256;
-        const uint32_t sum = row[255];
-        if (sum == 0) { failed = true; fail_at = j; break; }
-        uint32_t mult = divsum(p0, rc.high - rc.low);
-        if (mult == 0) {
-            if (rc.br.left() >= 4)
-                for (int i = 0; i < 4; ++i) rc.value = (rc.value << 8) | rc.br.get();
-            rc.low = 0;
-            rc.high = 0xFFFFFFFFu;
-            mult = rc.high / sum;
-            if (mult == 0) { failed = true; fail_at = j; break; }
+    uint32_t delivered = 0;
+    const uint32_t nmax = wvb_warp_max(total);
+    for (uint32_t j = 0; j < nmax; ++j) {
+        WVB_SYNCWARP();
+        if (j < total && !failed) {
+            const uint16_t *row = T.summed + p0 * 256;
+            const uint32_t sum = sumof(row, p0);
+            bool ok = sum != 0;
+            uint32_t mult = 0, index = 0;
+            if (ok) {
+                mult = (rc.high - rc.low) / sum;
+                if (mult == 0) {
+                    if (rc.br.left() >= 4)
+                        for (int i = 0; i < 4; ++i) rc.value = (rc.value << 8) | rc.br.get();
+                    rc.low = 0;
+                    rc.high = 0xFFFFFFFFu;
+                    mult = rc.high / sum;
+                    ok = mult != 0;
+                }
+            }
+            if (ok) {
+                index = (rc.value - rc.low) / mult;
+                ok = index < sum;
+            }
+            if (ok) {
+                uint32_t below, cur;
+                const int code = find(row, p0, index, below, cur);
+                emit(j, code);
+                delivered = j + 1;
+                rc.low += below * mult;
+                rc.high = rc.low + (cur - below) * mult - 1;
+                crc = crc * 3 + code;
+                if (mono) p0 = code & (bins - 1);
+                else { p0 = p1; p1 = code & (bins - 1); }
+                rc.normalize();
+            } else {
+                failed = true;
+                fail_at = j;
+            }
         }
-        const uint32_t index = (rc.value - rc.low) / mult;
-        if (index >= sum) { failed = true; fail_at = j; break; }
-        const int code = find(row, index);
-        emit(j, code);
-        const uint32_t below = code > 0 ? row[code - 1] : 0u;
-        rc.low += below * mult;
-        rc.high = rc.low + ((uint32_t)row[code] - below) * mult - 1;
-        crc = crc * 3 + code;
-        if (mono) p0 = code & (bins - 1);
-        else { p0 = p1; p1 = code & (bins - 1); }
-        rc.normalize();
     }
-    done(j);
+    done(delivered);
     crc_out = crc;
 }
 
