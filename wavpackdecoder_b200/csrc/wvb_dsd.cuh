@@ -102,9 +102,9 @@ k_dsd_high(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ de
 //     table (bins x 256 u16 cumulative sums, 512 B per history bin).
 // (2) k_dsd_fast_dec, one block per THREAD: the range decoder.  A warp-per-block decoder spends ~130 warp instructions per
 //     symbol on uniform work (ncu: issue-bound at 73%, profiles/r01_ncu_dsd_fast_warp_per_block.txt); per thread the same
-//     work advances 32 blocks.  Each thread keeps a 16-entry coarse index per bin (every 16th cumulative sum) in shared
-//     memory [word][thread]; the symbol lookup is a coarse count there plus a fine count over one 32-byte sector of its
-//     global table.
+//     work advances 32 blocks.  Each thread keeps an 8-entry coarse index per bin (every 32nd cumulative sum) in shared
+//     memory [word][thread]; the symbol lookup is a coarse count there plus a fine count over one 64-byte cell of its
+//     global table (one DRAM access).  The kernel is memory-latency bound, so the small index (16 B per bin) buys occupancy.
 constexpr int DSD_FAST_DEC_THREADS = 128;
 constexpr size_t DSD_FAST_TABLE_STRIDE = 32 * 512; // scratch bytes per block (room for 32 bins)
 
@@ -143,6 +143,9 @@ struct CoarseColumn { // word i of this thread's coarse index: [word][DSD_FAST_D
     __device__ __forceinline__ uint32_t &operator()(int i) { return base[i * DSD_FAST_DEC_THREADS]; }
 };
 
+// CW = coarse-index words per history bin: 8 (every 16th entry, 32-byte cells) or 4 (every 32nd entry, 64-byte cells).
+// Measured on B200, 160k blocks: 16 bins  CW=8 224 ms / CW=4 362 ms (more resident blocks thrash L2);  32 bins  CW=8 353 ms / CW=4 138 ms.
+template <int CW>
 static __global__ void __launch_bounds__(DSD_FAST_DEC_THREADS)
 k_dsd_fast_dec(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ descs, const uint32_t *__restrict__ order, uint32_t count,
                uint8_t *__restrict__ out, int out_format, wvb_block_result *__restrict__ results, const uint8_t *__restrict__ scratch,
@@ -162,8 +165,10 @@ k_dsd_fast_dec(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict_
     CoarseColumn CO{(uint32_t *)dsd_smem + threadIdx.x};
     if (good)
         for (int b = 0; b < bins; ++b)
-            for (int k = 0; k < 8; ++k) // entries 16*(2k)+15 and 16*(2k+1)+15 of bin b
-                CO(b * 8 + k) = (uint32_t)T.summed[b * 256 + 32 * k + 15] | ((uint32_t)T.summed[b * 256 + 32 * k + 31] << 16);
+            for (int k = 0; k < CW; ++k) { // two coarse entries per word: the last entries of cells 2k and 2k+1
+                constexpr int CELL = 128 / CW; // 16 or 32 table entries per cell
+                CO(b * CW + k) = (uint32_t)T.summed[b * 256 + 2 * CELL * k + CELL - 1] | ((uint32_t)T.summed[b * 256 + 2 * CELL * k + 2 * CELL - 1] << 16);
+            }
     DsdOut o;
     dsd_out_init(o, D, out, out_format);
     const bool mono = o.coded_ch == 1;
@@ -176,33 +181,25 @@ k_dsd_fast_dec(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict_
     uint32_t fail_at = total;
     const uint8_t *p = in + D.in_offset + D.sub_off[WVB_SUB_DSD];
     dsd_fast_decode(T, bins, p, D.sub_len[WVB_SUB_DSD], good ? M.at : 6u, mono, total,
-        [&](const uint16_t *, int p0) { return CO(p0 * 8 + 7) >> 16; }, // row[255] is the last coarse entry
+        [&](const uint16_t *, int p0) { return CO(p0 * CW + CW - 1) >> 16; }, // row[255] is the last coarse entry
         [&](const uint16_t *row, int p0, uint32_t index, uint32_t &below, uint32_t &cur) {
             const uint32_t idx2 = index | (index << 16);
             int c = 0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) c += __popc(__vcmpleu2(CO(p0 * 8 + k), idx2));
-            c >>= 4; // coarse cell 0..15 (index < row[255] keeps it below 16)
-            const uint4 *q = (const uint4 *)(row + 16 * c);
-            const uint4 a = q[0], b = q[1]; // the cell: 16 cumulative sums = one 32-byte sector of this block's table
-            const int f = (__popc(__vcmpleu2(a.x, idx2)) + __popc(__vcmpleu2(a.y, idx2)) + __popc(__vcmpleu2(a.z, idx2)) + __popc(__vcmpleu2(a.w, idx2)) +
-                           __popc(__vcmpleu2(b.x, idx2)) + __popc(__vcmpleu2(b.y, idx2)) + __popc(__vcmpleu2(b.z, idx2)) + __popc(__vcmpleu2(b.w, idx2))) >> 4;
-            // row[16c+f] and row[16c+f-1] straight out of the registers (no second trip to memory)
-            auto entry = [&](int e) { // e in 0..15
-                const bool hi = e >= 8;
-                const uint32_t w0 = hi ? b.x : a.x, w1 = hi ? b.y : a.y, w2 = hi ? b.z : a.z, w3 = hi ? b.w : a.w;
-                const int k = (e >> 1) & 3;
-                const uint32_t w = k == 0 ? w0 : k == 1 ? w1 : k == 2 ? w2 : w3;
-                return (e & 1) ? (w >> 16) : (w & 0xffffu);
-            };
-            cur = entry(f);
-            if (f > 0) below = entry(f - 1);
-            else if (c > 0) { // last entry of the previous cell = coarse entry c-1
-                const uint32_t cw = CO(p0 * 8 + ((c - 1) >> 1));
-                below = ((c - 1) & 1) ? (cw >> 16) : (cw & 0xffffu);
-            } else
-                below = 0;
-            return 16 * c + f;
+            for (int k = 0; k < CW; ++k) c += __popc(__vcmpleu2(CO(p0 * CW + k), idx2));
+            c >>= 4; // coarse cell (index < row[255] keeps it inside the row)
+            constexpr int CELL = 128 / CW;
+            const uint4 *q = (const uint4 *)(row + CELL * c); // the cell: 16 or 32 cumulative sums, contiguous in this block's table
+            int f = 0;
+#pragma unroll
+            for (int k = 0; k < CELL / 8; ++k) {
+                const uint4 v = q[k];
+                f += __popc(__vcmpleu2(v.x, idx2)) + __popc(__vcmpleu2(v.y, idx2)) + __popc(__vcmpleu2(v.z, idx2)) + __popc(__vcmpleu2(v.w, idx2));
+            }
+            const int code = CELL * c + (f >> 4);
+            cur = row[code]; // same lines as the cell just read
+            below = code > 0 ? row[code - 1] : 0u;
+            return code;
         },
         [&](uint32_t j, int code) {
             if (packed) { // four byte values per 32-bit store
@@ -296,11 +293,13 @@ inline int launch_dsd(int cls, const uint8_t *din, const wvb_block_desc *d_descs
         k_dsd_fast_build<<<(count + DSD_FAST_WARPS - 1) / DSD_FAST_WARPS, DSD_FAST_WARPS * 32, 0, s>>>(din, d_descs, d_order, count, tab, meta);
         if (cudaGetLastError() != cudaSuccess) return WVB_E_CUDA;
         if (launches) (*launches)++;
-        const size_t smem = (size_t)bins * 8 * sizeof(uint32_t) * DSD_FAST_DEC_THREADS;
+        const int cw = bins >= 32 ? 4 : 8;
+        const size_t smem = (size_t)bins * cw * sizeof(uint32_t) * DSD_FAST_DEC_THREADS;
         if (smem > smem_optin) return WVB_E_ARG;
-        if (cudaFuncSetAttribute((const void *)k_dsd_fast_dec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WVB_E_CUDA;
-        k_dsd_fast_dec<<<(count + DSD_FAST_DEC_THREADS - 1) / DSD_FAST_DEC_THREADS, DSD_FAST_DEC_THREADS, smem, s>>>(din, d_descs, d_order, count, dout,
-                                                                                                           out_format, dres, tab, meta);
+        auto kern = cw == 4 ? k_dsd_fast_dec<4> : k_dsd_fast_dec<8>;
+        if (cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WVB_E_CUDA;
+        kern<<<(count + DSD_FAST_DEC_THREADS - 1) / DSD_FAST_DEC_THREADS, DSD_FAST_DEC_THREADS, smem, s>>>(din, d_descs, d_order, count, dout, out_format, dres,
+                                                                                                    tab, meta);
     } else
         return WVB_E_ARG;
     if (cudaGetLastError() != cudaSuccess) return WVB_E_CUDA;
