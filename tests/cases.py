@@ -136,4 +136,11 @@ def corrupt_cases():
         bd = _blocks(dd)
         out.append(("dsd%d_flip" % m, flip(dd, bd[1][0] + bd[1][1] // 2, 0x04), 0, 4096))
         out.append(("dsd%d_flip_chunk3000" % m, flip(dd, bd[1][0] + bd[1][1] // 2, 0x04), 0, 3000))
+        # last block cut inside its ID_DSD_BLOCK payload: the reference keeps the previous block's (exhausted) DSD state
+        out.append(("dsd%d_truncated" % m, dd[:bd[-1][0] + 600], 0, 4096))
+    # metadata failure in the middle of a stream: ID_ENCODER_INFO (not optional) as first sub-block of block 1
+    bad = bytearray(data)
+    bad[bl[1][0] + 32] = 0x01
+    out.append(("bad_metadata_id_midstream", bytes(bad), 0, 4096))
+    out.append(("truncated_in_metadata", data[:bl[2][0] + 40], 0, 4096))
     return out

@@ -50,6 +50,7 @@ k_dsd_raw(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ des
     if (w >= count) return; // whole warp leaves together
     const uint32_t bi = order[w];
     const wvb_block_desc &D = descs[bi];
+    if (D.bflags & WVB_BF_MUTE_ALL) { dsd_stale_block(D, out, out_format, &results[bi], lane, 32); return; } // warp-uniform
     DsdOut o;
     dsd_out_init(o, D, out, out_format);
     const uint8_t *p = in + D.in_offset + D.sub_off[WVB_SUB_DSD] + 2;

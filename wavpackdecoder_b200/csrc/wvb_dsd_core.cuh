@@ -108,8 +108,24 @@ WVB_DEV void dsd_finish(const wvb_block_desc &D, wvb_block_result *res, int crc,
 }
 
 // ---- mode 0 -----------------------------------------------------------------------------------
+// A DSD block the reference decodes with state left over from an earlier block (WVB_BF_MUTE_ALL): zeros, then the last
+// piece is muted by the second pass exactly as after a CRC failure.  Flagged inexact.
+WVB_DEV void dsd_stale_block(const wvb_block_desc &D, uint8_t *out, int out_format, wvb_block_result *res, int lane, int nlanes)
+{
+    DsdOut o;
+    dsd_out_init(o, D, out, out_format);
+    const uint32_t total = D.block_samples * (uint32_t)o.coded_ch;
+    for (uint32_t j = (uint32_t)lane; j < total; j += (uint32_t)nlanes) o.put(j, 0);
+    if (lane == 0) {
+        wvb_block_desc tmp = D;
+        tmp.crc = 0; // crc below is -1: always a mismatch
+        dsd_finish(tmp, res, -1, false, 0, WVB_RF_INEXACT);
+    }
+}
+
 WVB_DEV void dsd_decode_raw(const uint8_t *in, const wvb_block_desc &D, uint8_t *out, int out_format, wvb_block_result *res)
 {
+    if (D.bflags & WVB_BF_MUTE_ALL) { dsd_stale_block(D, out, out_format, res, 0, 1); return; }
     DsdOut o;
     dsd_out_init(o, D, out, out_format);
     const uint8_t *p = in + D.in_offset + D.sub_off[WVB_SUB_DSD];

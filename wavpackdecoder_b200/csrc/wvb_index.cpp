@@ -410,6 +410,12 @@ bool unpack_init(Ctx &c)
     if (c.have_float) B.bflags |= WVB_BF_HAS_FLOAT_INFO;
     if (c.wvx_present) B.bflags |= WVB_BF_WVX_PRESENT;
     // state the device cannot rebuild from this block alone (quirk C-8)
+    if (h.block_samples != 0 && (h.flags & F_DSD) && !B.sub_off[WVB_SUB_DSD]) {
+        // wps.dsd is still the previous block's (exhausted) decoder: mode 0 writes nothing, modes 1/3 emit state-dependent bytes;
+        // the device writes zeros, mutes the last piece like the CRC failure would, and flags the block inexact
+        B.bflags |= WVB_BF_MUTE_ALL | WVB_BF_STALE_STATE;
+        B.smem_words = 0;
+    }
     const bool pcm = h.block_samples != 0 && !(h.flags & F_DSD);
     if (pcm) {
         if (!c.terms_from_this_block && c.num_terms > 0) B.bflags |= WVB_BF_STALE_STATE;
@@ -483,8 +489,12 @@ void index_reference_order(Ctx &c, uint32_t chunk, Sink &out)
         if (h.block_samples == 0 || !(h.flags & F_INITIAL) || c.sample_index >= h.block_index + (int64_t)h.block_samples) {
             if (!read_next_header(c)) brk = true;
             else if (h.block_samples == 0 || c.sample_index == h.block_index) {
-                if (!unpack_init(c)) { brk = true; I.stopped_early = 1; }
                 inited = true;
+                if (!unpack_init(c)) { // the call ends here; the next call decodes this header with the state left behind
+                    brk = true;
+                    I.stopped_early = 1;
+                    inited = false;
+                }
             } else
                 inited = false;
         }
