@@ -66,6 +66,18 @@ PCM_CASES = [
     ("shift8_24bit", 0, 4096, dict(bits=24, shift=8)),
     ("hybrid_24bit", 0, 4096, dict(kind=KIND_HYBRID, bits=24, hybrid_bitrate=6 * 256, terms=[18, 18, 2])),
     ("big_block", 0, 4096, dict(block_samples=88200, seconds=2.0)),
+    # the short lists of small terms libwavpack/FFmpeg write in their fast and default modes
+    ("ff_list_ff_default", 0, 4096, dict(terms=[18, 18, 2, 17, 3])),
+    ("ff_list_ff_nojoint", 0, 4096, dict(terms=[18, 17, -1, 3, 2], joint_stereo=0)),
+    ("ff_list_17_18_18_m2_2", 0, 4096, dict(terms=[17, 18, 18, -2, 2], deltas=[2, 3, 4, 5, 6])),
+    ("ff_list_17_17_m2_2_3", 0, 4096, dict(terms=[17, 17, -2, 2, 3])),
+    ("ff_list_fast", 0, 4096, dict(terms=[18, 17])),
+    ("ff_list_all_cross", 0, 4096, dict(terms=[-3, -1, 1, -2, -3], deltas=[1, 2, 3, 4, 5])),
+    ("ff_list_one_term", 0, 4096, dict(terms=[1])),
+    ("ff_list_mono", 0, 4096, dict(channels=1, terms=[18, 17, 3, 2, 1])),
+    ("ff_list_false_stereo", 0, 4096, dict(false_stereo=1, terms=[17, 18, 18, 1, 2], seconds=1.2)),
+    ("list_six_terms", 0, 4096, dict(terms=[18, 18, 2, 17, 3, 1])),
+    ("list_term4", 0, 4096, dict(terms=[18, 4, 2])),
 ]
 
 from _harness import KIND_DSD  # noqa: E402

@@ -51,3 +51,4 @@ def test_damaged_streams_follow_the_oracle(name, data, flags, chunk):
         assert any(r.rflags & 8 for r in res)
     else:
         assert np.array_equal(out, ref)
+

@@ -33,6 +33,11 @@ static __device__ __forceinline__ int wvb_clz(uint32_t x) { return __clz((int)x)
 #define WVB_SYNCWARP_MID() __syncwarp()
 #endif
 static __device__ __forceinline__ uint32_t wvb_warp_max(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
+static __device__ __forceinline__ uint32_t wvb_funnel_r(uint32_t lo, uint32_t hi, int s) { return __funnelshift_r(lo, hi, (uint32_t)s); }
+// the rounding term of apply_weight, kept in constant memory so that it is an operand of the multiply-add instead of
+// being rebuilt in registers for every pass
+static __device__ __constant__ long long wvb_k512 = 512;
+#define WVB_K512 wvb_k512
 #else
 #include <string.h>
 #define WVB_DEV inline
@@ -45,6 +50,8 @@ static inline int wvb_clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
 #define WVB_SYNCWARP() ((void)0)
 #define WVB_SYNCWARP_MID() ((void)0)
 static inline uint32_t wvb_warp_max(uint32_t v) { return v; }
+static inline uint32_t wvb_funnel_r(uint32_t lo, uint32_t hi, int s) { s &= 31; return s ? (lo >> s) | (hi << (32 - s)) : lo; }
+#define WVB_K512 512LL
 #endif
 
 namespace wvb {
@@ -91,46 +98,55 @@ WVB_DEV int restore_weight(int w8) // WordsUtils.cs:653-661, w8 already sign-ext
 // buffer with 0xFF on overrun, BitsUtils.cs:132-146).  A plain LSB-first window is bit-identical to
 // getbit/getbits.
 struct BitReader {
-    const uint8_t *next; // 4-byte aligned address of the next word to fetch
-    const uint8_t *end;
-    uint64_t bb;  // bit window, LSB = next bit
-    int bc;       // valid bits in bb
-    uint32_t nw;  // word fetched one refill ahead: its load latency overlaps the decode of the bits before it
+    const uint8_t *base; // 4-byte aligned address of stream word 0
+    uint32_t idx;        // next word to fetch
+    uint32_t full_end;   // words [0, full_end) lie wholly inside the stream
+    uint32_t tailw;      // word `full_end`: the stream's last 1..3 bytes with 0xFF above them (all ones if there are none)
+    uint32_t w0, w1;     // window: bit `pos` of w1:w0 is the next bit of the stream
+    uint32_t q0, q1;     // the two words after the window.  q1 is the load in flight: it is first read (moved to q0) at
+                         // the next shift, a whole word later, so its latency is never waited for; q0 extends the window
+                         // to 96 bits for peek_far() without touching the register a load is pending on
+    int pos;             // < 32 after refill()
 
-    WVB_DEV uint32_t load_word() // bytes at or past `end` read as 0xFF (this three-way form measured faster than a single range test)
+    WVB_DEV uint32_t load_word() // branch-free, so that shift() can be predicated instead of a divergent branch
     {
-        uint32_t x;
-        if (next + 4 <= end) x = wvb_ld_u32(next);
-        else if (next >= end) x = 0xFFFFFFFFu;
-        else x = wvb_ld_u32(next) | (0xFFFFFFFFu << (8 * (int)(end - next)));
-        next += 4;
+        uint32_t x = idx == full_end ? tailw : 0xFFFFFFFFu;
+        if (idx < full_end) x = wvb_ld_u32(base + 4 * (size_t)idx);
+        ++idx;
         return x;
     }
     WVB_DEV void init(const uint8_t *s, uint32_t len)
     {
-        end = s + len;
-        const int mis = (int)((uintptr_t)s & 3);
-        next = s - mis;
-        const uint32_t x = load_word();
-        bb = x >> (8 * mis);
-        bc = 32 - 8 * mis;
-        nw = load_word();
+        const uint32_t mis = (uint32_t)((uintptr_t)s & 3);
+        base = s - mis;
+        const uint32_t total = mis + len, r = total & 3u;
+        full_end = total >> 2;
+        tailw = r ? (wvb_ld_u32(base + 4 * (size_t)full_end) | (0xFFFFFFFFu << (8 * r))) : 0xFFFFFFFFu;
+        idx = 0;
+        w0 = load_word();
+        w1 = load_word();
+        q0 = load_word();
+        q1 = load_word();
+        pos = 8 * (int)mis;
     }
-    WVB_DEV void refill() // afterwards bc >= 33
+    WVB_DEV void shift() { w0 = w1; w1 = q0; q0 = q1; q1 = load_word(); pos -= 32; }
+    WVB_DEV void refill() // pos < 96 on entry, < 32 on return: peek() then holds 32 valid bits, peek_far() 64 - pos
     {
-        if (bc <= 32) {
-            bb |= (uint64_t)nw << bc;
-            bc += 32;
-            nw = load_word();
-        }
+        if (pos >= 64) shift(); // rare: more than 32 bits consumed since the last refill
+        if (pos >= 32) shift();
     }
-    WVB_DEV void consume(int n) { bb >>= n; bc -= n; }
-    WVB_DEV uint32_t peek() const { return (uint32_t)bb; }
-    WVB_DEV uint32_t getbit() { refill(); const uint32_t b = (uint32_t)bb & 1u; consume(1); return b; }
+    WVB_DEV void consume(int n) { pos += n; }
+    WVB_DEV uint32_t peek() const { return wvb_funnel_r(w0, w1, pos); } // needs pos < 32
+    WVB_DEV uint32_t peek_far() const                                   // needs pos < 64; 32 valid bits
+    {
+        const bool far = pos >= 32;
+        return wvb_funnel_r(far ? w1 : w0, far ? q0 : w1, pos);
+    }
+    WVB_DEV uint32_t getbit() { refill(); const uint32_t b = peek() & 1u; consume(1); return b; }
     WVB_DEV uint32_t getbits(int n) // 0 <= n <= 32
     {
         refill();
-        const uint32_t v = n >= 32 ? (uint32_t)bb : ((uint32_t)bb & ((1u << n) - 1u));
+        const uint32_t v = n >= 32 ? peek() : (peek() & ((1u << n) - 1u));
         consume(n);
         return v;
     }
@@ -237,7 +253,7 @@ template <bool HYB, bool STEREO, int CH> WVB_DEV bool decode_word(BitReader &br,
     }
 
     if (ok && !done) {
-        br.refill(); // >= 33 bits
+        br.refill();
         int ones = 0;
         if (w.hold == 2) { // WordsUtils.cs:354-358
             w.hold = 0;
@@ -250,7 +266,6 @@ template <bool HYB, bool STEREO, int CH> WVB_DEV bool decode_word(BitReader &br,
                     uint32_t v = 0;
                     ok = read_gamma(br, v);
                     t = (int)v + 16;
-                    br.refill();
                 }
             } else
                 br.consume(t + 1);
@@ -292,41 +307,41 @@ template <bool HYB, bool STEREO, int CH> WVB_DEV bool decode_word(BitReader &br,
                 }
             }
 
-            uint32_t mid;
+            uint32_t mid, sign;
             bool lossless_code = true;
             if constexpr (HYB) lossless_code = w.errlim[CH] == 0;
-            if (lossless_code) { // read_code, WordsUtils.cs:546-570
-                const uint32_t range = high - low;
-                mid = low;
-                if (range) {
-                    const int bitcount = 32 - wvb_clz(range);
-                    if (bitcount >= 31)
-                        mid = read_code_wide(br, low, range);
-                    else {
-                        const uint32_t extras = (1u << bitcount) - range - 1u;
-                        if (br.bc <= bitcount) br.refill(); // need bitcount-1 code bits + 1 extra + 1 sign
-                        uint32_t code = br.peek() & ((1u << (bitcount - 1)) - 1u);
-                        br.consume(bitcount - 1);
-                        if (code >= extras) {
-                            code = (code << 1) - extras + (br.peek() & 1u);
-                            br.consume(1);
-                        }
-                        mid = low + code;
+            const uint32_t range = high - low;
+            const int bitcount = 32 - wvb_clz(range);
+            if (lossless_code && bitcount < 31) {
+                // read_code (WordsUtils.cs:546-570) and the sign bit (494-497) out of one 32-bit look-ahead: at most
+                // bitcount-1 code bits, one extra bit and the sign, 31 bits in all
+                const uint32_t pk = br.peek_far(); // pos <= 31 + 16 here
+                const uint32_t extras = (1u << bitcount) - range - 1u;
+                int nbits = bitcount > 0 ? bitcount - 1 : 0;
+                uint32_t code = pk & ((1u << nbits) - 1u);
+                if (range != 0 && code >= extras) {
+                    code = (code << 1) - extras + ((pk >> nbits) & 1u);
+                    ++nbits;
+                }
+                mid = low + code;
+                sign = (pk >> nbits) & 1u;
+                br.consume(nbits + 1);
+            } else {
+                if (lossless_code)
+                    mid = read_code_wide(br, low, range);
+                else { // WordsUtils.cs:477-492
+                    uint32_t lim = 0;
+                    if constexpr (HYB) lim = (uint32_t)w.errlim[CH];
+                    mid = (uint32_t)(((uint64_t)high + low + 1) >> 1);
+                    while (high - low > lim) {
+                        if (br.getbit()) low = mid;
+                        else high = mid - 1;
+                        mid = (uint32_t)(((uint64_t)high + low + 1) >> 1);
                     }
                 }
-            } else { // WordsUtils.cs:477-492
-                uint32_t lim = 0;
-                if constexpr (HYB) lim = (uint32_t)w.errlim[CH];
-                mid = (uint32_t)(((uint64_t)high + low + 1) >> 1);
-                while (high - low > lim) {
-                    if (br.getbit()) low = mid;
-                    else high = mid - 1;
-                    mid = (uint32_t)(((uint64_t)high + low + 1) >> 1);
-                }
+                sign = br.getbit();
             }
-            if (br.bc == 0) br.refill();
-            out = (br.peek() & 1u) ? (int)~mid : (int)mid; // WordsUtils.cs:494-497
-            br.consume(1);
+            out = sign ? (int)~mid : (int)mid; // WordsUtils.cs:494-497
             if constexpr (HYB) {
                 if (flags & F_HYB_BITRATE) // WordsUtils.cs:501-502
                     w.slow[CH] = w.slow[CH] - ((w.slow[CH] + 128) >> 8) + mylog2(mid);
@@ -337,18 +352,29 @@ template <bool HYB, bool STEREO, int CH> WVB_DEV bool decode_word(BitReader &br,
 }
 
 // ---- decorrelation ---------------------------------------------------------------------------
-WVB_DEV int apply_weight(int w, int s) { return (int)(((int64_t)w * (int64_t)s + 512) >> 10); }
+WVB_DEV int apply_weight(int w, int s) { return (int)(((int64_t)w * (int64_t)s + WVB_K512) >> 10); }
 WVB_DEV int upd_weight(int w, int delta, int s, int in) // UnpackUtils.cs:707-713
 {
-    if (s != 0 && in != 0) w += ((s ^ in) < 0) ? -delta : delta;
+    const int sg = (s ^ in) >> 31; // -1 when the signs differ: w -= delta, else w += delta
+    const int d = delta ^ sg;
+#ifdef __CUDA_ARCH__
+    // spelled out so that the two non-zero tests fold into one predicate on a single add (the compiler otherwise
+    // builds the increment through a chain of selects: 9 instructions per weight instead of 6)
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %1, 0;\n\tsetp.ne.and.s32 p, %2, 0, p;\n\t@p sub.s32 %0, %0, %3;\n\t@p add.s32 %0, %0, %4;\n\t}"
+        : "+r"(w) : "r"(s), "r"(in), "r"(sg), "r"(d));
+#else
+    if (s != 0 && in != 0) w += d - sg;
+#endif
     return w;
 }
 WVB_DEV int upd_weight_clip(int w, int delta, int s, int in) // UnpackUtils.cs:776-785
 {
-    if (s != 0 && in != 0) {
-        if ((s ^ in) < 0) { w -= delta; if (w < -1024) w = -1024; }
-        else { w += delta; if (w > 1024) w = 1024; }
-    }
+    // cross-channel weights never leave [-1024, 1024] (restore_weight's range, and every update clips), so clipping both
+    // sides equals the reference's one-sided clip
+    const int sg = (s ^ in) >> 31;
+    int t = w + (delta ^ sg) - sg;
+    t = t < -1024 ? -1024 : t > 1024 ? 1024 : t;
+    if (s != 0 && in != 0) w = t;
     return w;
 }
 
@@ -585,6 +611,7 @@ template <bool STEREO, int... TERMS> struct FixedDecorr {
         }
     }
 };
+
 
 // ---- fixup (UnpackUtils.cs:1251-1404, FloatUtils.cs:32-56) -----------------------------------
 struct Fixup {
