@@ -33,7 +33,6 @@ static __device__ __forceinline__ int wvb_clz(uint32_t x) { return __clz((int)x)
 #define WVB_SYNCWARP_MID() __syncwarp()
 #endif
 static __device__ __forceinline__ uint32_t wvb_warp_max(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
-static __device__ __forceinline__ uint32_t wvb_funnel_r(uint32_t lo, uint32_t hi, int s) { return __funnelshift_r(lo, hi, (uint32_t)s); }
 // the rounding term of apply_weight, kept in constant memory so that it is an operand of the multiply-add instead of
 // being rebuilt in registers for every pass
 static __device__ __constant__ long long wvb_k512 = 512;
@@ -50,7 +49,6 @@ static inline int wvb_clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
 #define WVB_SYNCWARP() ((void)0)
 #define WVB_SYNCWARP_MID() ((void)0)
 static inline uint32_t wvb_warp_max(uint32_t v) { return v; }
-static inline uint32_t wvb_funnel_r(uint32_t lo, uint32_t hi, int s) { s &= 31; return s ? (lo >> s) | (hi << (32 - s)) : lo; }
 #define WVB_K512 512LL
 #endif
 
@@ -102,13 +100,11 @@ struct BitReader {
     uint32_t idx;        // next word to fetch
     uint32_t full_end;   // words [0, full_end) lie wholly inside the stream
     uint32_t tailw;      // word `full_end`: the stream's last 1..3 bytes with 0xFF above them (all ones if there are none)
-    uint32_t w0, w1;     // window: bit `pos` of w1:w0 is the next bit of the stream
-    uint32_t q0, q1;     // the two words after the window.  q1 is the load in flight: it is first read (moved to q0) at
-                         // the next shift, a whole word later, so its latency is never waited for; q0 extends the window
-                         // to 96 bits for peek_far() without touching the register a load is pending on
-    int pos;             // < 32 after refill()
+    uint32_t w0, w1;     // window: bit `pos` of w1:w0 is the next bit of the stream; 64 - pos bits are valid
+    uint32_t nw;         // word fetched one refill ahead: its load latency overlaps the decode of the bits before it
+    int pos;             // 0..63 (every consumer leaves at least one valid bit or refills first)
 
-    WVB_DEV uint32_t load_word() // branch-free, so that shift() can be predicated instead of a divergent branch
+    WVB_DEV uint32_t load_word()
     {
         uint32_t x = idx == full_end ? tailw : 0xFFFFFFFFu;
         if (idx < full_end) x = wvb_ld_u32(base + 4 * (size_t)idx);
@@ -125,23 +121,50 @@ struct BitReader {
         idx = 0;
         w0 = load_word();
         w1 = load_word();
-        q0 = load_word();
-        q1 = load_word();
+        nw = load_word();
         pos = 8 * (int)mis;
+#ifdef __CUDA_ARCH__
+        // Read the three words once before the sample loop.  All stream loads share one hardware scoreboard; a load still
+        // formally pending on w0/w1 at loop entry makes the first peek of EVERY iteration wait on that scoreboard, i.e.
+        // on the prefetch issued just before it.
+        // (the ballot's result feeds a condition that never holds, only so that the read is not optimised away)
+        uint32_t seen;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\tvote.sync.ballot.b32 %0, p, 0xffffffff;\n\t}" : "=r"(seen) : "r"(w0 | w1 | nw));
+        if (seen == 0x5a5a5a5au && len == 0xffffffffu) ++pos;
+#endif
     }
-    WVB_DEV void shift() { w0 = w1; w1 = q0; q0 = q1; q1 = load_word(); pos -= 32; }
-    WVB_DEV void refill() // pos < 96 on entry, < 32 on return: peek() then holds 32 valid bits, peek_far() 64 - pos
+    WVB_DEV void refill() // afterwards pos < 32: at least 33 valid bits
     {
-        if (pos >= 64) shift(); // rare: more than 32 bits consumed since the last refill
-        if (pos >= 32) shift();
+        if (pos >= 32) {
+#ifdef __CUDA_ARCH__
+            // Written out so that the load lands in `nw` itself.  Left to the compiler, the fetched word goes to a
+            // temporary that is copied into `nw` at once, which waits out the whole load latency at every refill (ncu:
+            // 1.3-1.8 long-scoreboard stall cycles per issued instruction) instead of overlapping it with the next word.
+            asm volatile("{\n\t"
+                         ".reg .pred p, q;\n\t"
+                         ".reg .u64 a;\n\t"
+                         "mov.u32 %0, %1;\n\t"
+                         "mov.u32 %1, %2;\n\t"
+                         "setp.eq.u32 q, %3, %5;\n\t"
+                         "selp.u32 %2, %6, 0xffffffff, q;\n\t"
+                         "setp.lt.u32 p, %3, %5;\n\t"
+                         "mad.wide.u32 a, %3, 4, %7;\n\t"
+                         "@p ld.global.nc.u32 %2, [a];\n\t"
+                         "add.u32 %3, %3, 1;\n\t"
+                         "sub.s32 %4, %4, 32;\n\t"
+                         "}"
+                         : "+r"(w0), "+r"(w1), "+r"(nw), "+r"(idx), "+r"(pos)
+                         : "r"(full_end), "r"(tailw), "l"(base));
+#else
+            w0 = w1;
+            w1 = nw;
+            nw = load_word();
+            pos -= 32;
+#endif
+        }
     }
     WVB_DEV void consume(int n) { pos += n; }
-    WVB_DEV uint32_t peek() const { return wvb_funnel_r(w0, w1, pos); } // needs pos < 32
-    WVB_DEV uint32_t peek_far() const                                   // needs pos < 64; 32 valid bits
-    {
-        const bool far = pos >= 32;
-        return wvb_funnel_r(far ? w1 : w0, far ? q0 : w1, pos);
-    }
+    WVB_DEV uint32_t peek() const { return (uint32_t)((((uint64_t)w1 << 32) | w0) >> pos); } // the next min(32, 64 - pos) bits
     WVB_DEV uint32_t getbit() { refill(); const uint32_t b = peek() & 1u; consume(1); return b; }
     WVB_DEV uint32_t getbits(int n) // 0 <= n <= 32
     {
@@ -315,7 +338,8 @@ template <bool HYB, bool STEREO, int CH> WVB_DEV bool decode_word(BitReader &br,
             if (lossless_code && bitcount < 31) {
                 // read_code (WordsUtils.cs:546-570) and the sign bit (494-497) out of one 32-bit look-ahead: at most
                 // bitcount-1 code bits, one extra bit and the sign, 31 bits in all
-                const uint32_t pk = br.peek_far(); // pos <= 31 + 16 here
+                if (br.pos + bitcount > 62) br.refill(); // rare below 17-bit codes: pos <= 31 + 16 here
+                const uint32_t pk = br.peek();
                 const uint32_t extras = (1u << bitcount) - range - 1u;
                 int nbits = bitcount > 0 ? bitcount - 1 : 0;
                 uint32_t code = pk & ((1u << nbits) - 1u);
