@@ -253,29 +253,29 @@ WVB_DEV uint32_t read_code_wide(BitReader &br, uint32_t low, uint32_t range)
 template <bool HYB, bool STEREO, int CH> WVB_DEV bool decode_word(BitReader &br, Words<HYB> &w, uint32_t flags, int &out)
 {
     int *med = w.m[CH];
-    bool ok = true, done = false;
+    int st = 1; // 1: a code follows; 0: the word is a zero of a run; -1: the reference's `break` (EOF / bad code)
     out = 0;
     if (((w.m[0][0] | w.m[1][0]) & ~1) == 0 && w.hold == 0) { // zero-run regime, WordsUtils.cs:304-352
         if (w.zeros_acc > 0) {
-            if (--w.zeros_acc > 0) done = true;
+            if (--w.zeros_acc > 0) st = 0;
         } else {
             uint32_t z = 0;
-            ok = read_gamma(br, z);
-            if (ok) {
+            if (!read_gamma(br, z)) st = -1;
+            else {
                 w.zeros_acc = z;
                 if (z > 0) {
                     w.m[0][0] = w.m[0][1] = w.m[0][2] = 0;
                     w.m[1][0] = w.m[1][1] = w.m[1][2] = 0;
-                    done = true;
+                    st = 0;
                 }
             }
         }
-        if (done) {
-            if constexpr (HYB) w.slow[CH] -= (w.slow[CH] + 128) >> 8;
+        if constexpr (HYB) {
+            if (st == 0) w.slow[CH] -= (w.slow[CH] + 128) >> 8;
         }
     }
 
-    if (ok && !done) {
+    if (st > 0) {
         br.refill();
         int ones = 0;
         if (w.hold == 2) { // WordsUtils.cs:354-358
@@ -284,10 +284,10 @@ template <bool HYB, bool STEREO, int CH> WVB_DEV bool decode_word(BitReader &br,
             int t = wvb_ffs(~br.peek()) - 1;
             if ((unsigned)t >= 16u) {
                 br.consume(16);
-                if (br.getbit()) ok = false; // 17 ones: end of stream
+                if (br.getbit()) st = -1; // 17 ones: end of stream
                 else {
                     uint32_t v = 0;
-                    ok = read_gamma(br, v);
+                    if (!read_gamma(br, v)) st = -1;
                     t = (int)v + 16;
                 }
             } else
@@ -297,7 +297,7 @@ template <bool HYB, bool STEREO, int CH> WVB_DEV bool decode_word(BitReader &br,
             ones = (t >> 1) + h1;
         }
 
-        if (ok) {
+        if (st > 0) {
             if constexpr (HYB && CH == 0) update_error_limit<STEREO>(w, flags); // WordsUtils.cs:430-431
 
             uint32_t low, high; // WordsUtils.cs:433-475
@@ -372,7 +372,7 @@ template <bool HYB, bool STEREO, int CH> WVB_DEV bool decode_word(BitReader &br,
             }
         }
     }
-    return ok;
+    return st >= 0;
 }
 
 // ---- decorrelation ---------------------------------------------------------------------------
@@ -954,9 +954,10 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
     // All 32 lanes of a warp iterate together (warp-max trip count) and re-join at the top of every sample:
     // a lane left behind by a divergent branch must not be allowed to run the rest of its block alone.
     const uint32_t nmax = wvb_warp_max(n);
+    uint32_t live_n = n; // drops to 0 when the lane faults: it then idles through the remaining iterations
     for (uint32_t t = 0; t < nmax; ++t) {
         WVB_SYNCWARP();
-        const bool act = t < n && !fault;
+        const bool act = t < live_n;
         if (act && t == next_ev) {
             dec.truncate(SM, nterms);
             uint32_t ps, pe;
@@ -964,54 +965,53 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
             next_ev = next_piece_event<STEREO>(t, ps, pe);
         }
         int a = 0, b = 0;
-        bool ok = act;
-        if (!eof_fault) {
-            if (ok) ok = decode_word<HYB, STEREO, 0>(br, w, flags, a);
+        bool got = act && !eof_fault;
+        if (got) got = decode_word<HYB, STEREO, 0>(br, w, flags, a);
+        WVB_SYNCWARP_MID();
+        if (STEREO) {
+            if (got) got = decode_word<HYB, STEREO, 1>(br, w, flags, b);
             WVB_SYNCWARP_MID();
-            if (STEREO) {
-                if (ok) ok = decode_word<HYB, STEREO, 1>(br, w, flags, b);
-                WVB_SYNCWARP_MID();
-            }
-            if (act && !ok) { // get_words came back short (WordsUtils.cs:323,383,393): the reference still runs the passes and
-                eof_fault = true; // the CRC over the rest of the chunk, reading whatever the caller's buffer held.  We model
-                ok = true;        // those stale entries as zeros (exact for silence, and a CRC mismatch either way otherwise).
-                a = b = 0;
-            }
         }
-        if (ok) {
+        if (act) {
+            if (!got && !eof_fault) { // get_words came back short (WordsUtils.cs:323,383,393): the reference still runs the
+                eof_fault = true;     // passes and the CRC over the rest of the chunk, reading whatever the caller's buffer
+                a = b = 0;            // held.  We model those stale entries as zeros (exact for silence, and a CRC
+            }                         // mismatch either way otherwise).
             dec.frame(SM, nterms, t, a, b);
             if (joint) { b -= (a >> 1); a += b; } // UnpackUtils.cs:615 (App. E-9)
             const int aa = a < 0 ? -a : a, ab = b < 0 ? -b : b;
-            if (aa > mute_limit || (STEREO && ab > mute_limit)) ok = false;
-        }
-        if (ok) {
-            crc = crc * 3 + a;
-            if (STEREO) crc = crc * 3 + b;
-        }
-        if (ok && !eof_fault) {
-            if (fast16) {
-                *(uint32_t *)op = ((uint32_t)shl32(a, fx.shift) & 0xffffu) | ((uint32_t)shl32(b, fx.shift) << 16);
-            } else {
-                int va, vb = 0;
-                if (GENFIX) {
-                    va = fixup_value(fx, a, wvx, crc_x);
-                    if (STEREO) vb = fixup_value(fx, b, wvx, crc_x);
-                } else {
-                    va = shl32(a, fx.shift);
-                    if (STEREO) vb = shl32(b, fx.shift);
+            bool stop = aa > mute_limit || (STEREO && ab > mute_limit);
+            if (!stop) {
+                crc = crc * 3 + a;
+                if (STEREO) crc = crc * 3 + b;
+                if (!eof_fault) {
+                    if (fast16) {
+                        *(uint32_t *)op = ((uint32_t)shl32(a, fx.shift) & 0xffffu) | ((uint32_t)shl32(b, fx.shift) << 16);
+                    } else {
+                        int va, vb = 0;
+                        if (GENFIX) {
+                            va = fixup_value(fx, a, wvx, crc_x);
+                            if (STEREO) vb = fixup_value(fx, b, wvx, crc_x);
+                        } else {
+                            va = shl32(a, fx.shift);
+                            if (STEREO) vb = shl32(b, fx.shift);
+                        }
+                        store_unit(op, va, unit, add128);
+                        if (out_ch == 2) store_unit(op + unit, STEREO ? vb : va, unit, add128); // FALSE_STEREO duplicates (UnpackUtils.cs:668-680)
+                    }
+                    op += frame_bytes;
+                } else { // the modelled remainder of the chunk ends with the piece
+                    uint32_t ps, pe;
+                    piece_bounds(D, n, t, ps, pe);
+                    stop = t + 1 == pe;
                 }
-                store_unit(op, va, unit, add128);
-                if (out_ch == 2) store_unit(op + unit, STEREO ? vb : va, unit, add128); // FALSE_STEREO duplicates (UnpackUtils.cs:668-680)
             }
-            op += frame_bytes;
+            if (stop) {
+                fault = true;
+                fault_t = t;
+                live_n = 0;
+            }
         }
-        if (act && !ok) fault = true;
-        if (act && eof_fault && !fault) { // the modelled remainder of the chunk ends with the piece
-            uint32_t ps, pe;
-            piece_bounds(D, n, t, ps, pe);
-            if (t + 1 == pe) fault = true;
-        }
-        if (fault && act) fault_t = t;
     }
 
     if (fault) { // mute from the start of the caller chunk that contains the fault (UnpackUtils.cs:649-664, App. E-10)
