@@ -276,58 +276,41 @@ template <bool HYB, bool STEREO, int CH> WVB_DEV bool decode_word(BitReader &br,
     }
 
     if (st > 0) {
+        // The hold flags, the unary count and the three medians are computed without branches: the 32 lanes of a warp
+        // rarely agree on `ones`, so every branch here would be walked on both sides anyway, plus its (re)convergence cost.
         br.refill();
-        int ones = 0;
-        if (w.hold == 2) { // WordsUtils.cs:354-358
-            w.hold = 0;
-        } else { // WordsUtils.cs:361-428
-            int t = wvb_ffs(~br.peek()) - 1;
-            if ((unsigned)t >= 16u) {
-                br.consume(16);
-                if (br.getbit()) st = -1; // 17 ones: end of stream
-                else {
-                    uint32_t v = 0;
-                    if (!read_gamma(br, v)) st = -1;
-                    t = (int)v + 16;
-                }
-            } else
-                br.consume(t + 1);
-            const int h1 = w.hold == 1;
-            w.hold = (t & 1) ? 1 : 2;
-            ones = (t >> 1) + h1;
+        const bool held0 = w.hold == 2; // a zero left over from the previous word: no unary prefix (WordsUtils.cs:354-358)
+        int t = wvb_ffs(~br.peek()) - 1; // WordsUtils.cs:361-428
+        int nb = t + 1;
+        if (!held0 && (unsigned)t >= 16u) { // escape: 16 ones, then a zero and a gamma-coded count, or a 17th one = end of stream
+            br.consume(16);
+            nb = 0;
+            if (br.getbit()) st = -1;
+            else {
+                uint32_t v = 0;
+                if (!read_gamma(br, v)) st = -1;
+                t = (int)v + 16;
+            }
         }
+        br.consume(held0 ? 0 : nb);
+        const int ones = held0 ? 0 : (t >> 1) + (w.hold == 1 ? 1 : 0);
+        w.hold = held0 ? 0 : 2 - (t & 1);
 
         if (st > 0) {
             if constexpr (HYB && CH == 0) update_error_limit<STEREO>(w, flags); // WordsUtils.cs:430-431
 
             uint32_t low, high; // WordsUtils.cs:433-475
             {
-                const int g0 = (med[0] >> 4) + 1;
-                if (ones == 0) {
-                    low = 0;
-                    high = (uint32_t)g0 - 1;
-                    med[0] -= ((med[0] + 126) >> 7) * 2;
-                } else {
-                    low = (uint32_t)g0;
-                    med[0] += ((med[0] + 128) >> 7) * 5;
-                    const int g1 = (med[1] >> 4) + 1;
-                    if (ones == 1) {
-                        high = low + (uint32_t)g1 - 1;
-                        med[1] -= ((med[1] + 62) >> 6) * 2;
-                    } else {
-                        low += (uint32_t)g1;
-                        med[1] += ((med[1] + 64) >> 6) * 5;
-                        const int g2 = (med[2] >> 4) + 1;
-                        if (ones == 2) {
-                            high = low + (uint32_t)g2 - 1;
-                            med[2] -= ((med[2] + 30) >> 5) * 2;
-                        } else {
-                            low += (uint32_t)((ones - 2) * g2);
-                            high = low + (uint32_t)g2 - 1;
-                            med[2] += ((med[2] + 32) >> 5) * 5;
-                        }
-                    }
-                }
+                const int m0 = med[0], m1 = med[1], m2 = med[2];
+                const int g0 = (m0 >> 4) + 1, g1 = (m1 >> 4) + 1, g2 = (m2 >> 4) + 1;
+                const bool p1 = ones >= 1, p2 = ones >= 2, p3 = ones >= 3;
+                med[0] = m0 + ((m0 + (p1 ? 128 : 126)) >> 7) * (p1 ? 5 : -2);             // ones == 0 decrements m0, else incremented
+                if (p1) med[1] = m1 + ((m1 + (p2 ? 64 : 62)) >> 6) * (p2 ? 5 : -2);       // ones == 1 decrements m1, above increments
+                if (p2) med[2] = m2 + ((m2 + (p3 ? 32 : 30)) >> 5) * (p3 ? 5 : -2);       // ones == 2 decrements m2, above increments
+                low = p1 ? (uint32_t)g0 : 0u;
+                if (p2) low += (uint32_t)g1;
+                if (p3) low += (uint32_t)((ones - 2) * g2);
+                high = low + (uint32_t)(p2 ? g2 : p1 ? g1 : g0) - 1u;
             }
 
             uint32_t mid, sign;
