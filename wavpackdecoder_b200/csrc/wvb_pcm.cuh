@@ -304,12 +304,11 @@ template <bool HYB, bool STEREO, int CH> WVB_DEV bool decode_word(BitReader &br,
                 const int m0 = med[0], m1 = med[1], m2 = med[2];
                 const int g0 = (m0 >> 4) + 1, g1 = (m1 >> 4) + 1, g2 = (m2 >> 4) + 1;
                 const bool p1 = ones >= 1, p2 = ones >= 2, p3 = ones >= 3;
-                med[0] = m0 + ((m0 + (p1 ? 128 : 126)) >> 7) * (p1 ? 5 : -2);             // ones == 0 decrements m0, else incremented
-                if (p1) med[1] = m1 + ((m1 + (p2 ? 64 : 62)) >> 6) * (p2 ? 5 : -2);       // ones == 1 decrements m1, above increments
-                if (p2) med[2] = m2 + ((m2 + (p3 ? 32 : 30)) >> 5) * (p3 ? 5 : -2);       // ones == 2 decrements m2, above increments
-                low = p1 ? (uint32_t)g0 : 0u;
-                if (p2) low += (uint32_t)g1;
-                if (p3) low += (uint32_t)((ones - 2) * g2);
+                // ones == 0 decrements m0, more increments it; m1 moves only from ones >= 1 (down at 1, up above), m2 from 2
+                med[0] = m0 + ((m0 + (p1 ? 128 : 126)) >> 7) * (p1 ? 5 : -2);
+                med[1] = m1 + ((m1 + (p2 ? 64 : 62)) >> 6) * (p1 ? (p2 ? 5 : -2) : 0);
+                med[2] = m2 + ((m2 + (p3 ? 32 : 30)) >> 5) * (p2 ? (p3 ? 5 : -2) : 0);
+                low = (p1 ? (uint32_t)g0 : 0u) + (p2 ? (uint32_t)g1 : 0u) + (p3 ? (uint32_t)((ones - 2) * g2) : 0u);
                 high = low + (uint32_t)(p2 ? g2 : p1 ? g1 : g0) - 1u;
             }
 
