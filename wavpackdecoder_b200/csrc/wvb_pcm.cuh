@@ -940,25 +940,23 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
     for (uint32_t t = 0; t < nmax; ++t) {
         WVB_SYNCWARP();
         const bool act = t < live_n;
-        if (act && t == next_ev) {
-            dec.truncate(SM, nterms);
-            uint32_t ps, pe;
-            piece_bounds(D, n, t, ps, pe);
-            next_ev = next_piece_event<STEREO>(t, ps, pe);
-        }
-        int a = 0, b = 0;
-        bool got = act && !eof_fault;
-        if (got) got = decode_word<HYB, STEREO, 0>(br, w, flags, a);
-        WVB_SYNCWARP_MID();
-        if (STEREO) {
-            if (got) got = decode_word<HYB, STEREO, 1>(br, w, flags, b);
-            WVB_SYNCWARP_MID();
-        }
         if (act) {
-            if (!got && !eof_fault) { // get_words came back short (WordsUtils.cs:323,383,393): the reference still runs the
-                eof_fault = true;     // passes and the CRC over the rest of the chunk, reading whatever the caller's buffer
-                a = b = 0;            // held.  We model those stale entries as zeros (exact for silence, and a CRC
-            }                         // mismatch either way otherwise).
+            if (t == next_ev) {
+                dec.truncate(SM, nterms);
+                uint32_t ps, pe;
+                piece_bounds(D, n, t, ps, pe);
+                next_ev = next_piece_event<STEREO>(t, ps, pe);
+            }
+            int a = 0, b = 0;
+            if (!eof_fault) {
+                // the second word is decoded even when the first came back short: the state it disturbs is never used again
+                bool got = decode_word<HYB, STEREO, 0>(br, w, flags, a);
+                if (STEREO) got &= decode_word<HYB, STEREO, 1>(br, w, flags, b);
+                if (!got) {           // get_words came back short (WordsUtils.cs:323,383,393): the reference still runs the
+                    eof_fault = true; // passes and the CRC over the rest of the chunk, reading whatever the caller's buffer
+                    a = b = 0;        // held.  We model those stale entries as zeros (exact for silence, and a CRC
+                }                     // mismatch either way otherwise).
+            }
             dec.frame(SM, nterms, t, a, b);
             if (joint) { b -= (a >> 1); a += b; } // UnpackUtils.cs:615 (App. E-9)
             const int aa = a < 0 ? -a : a, ab = b < 0 ? -b : b;
