@@ -285,18 +285,19 @@ template <bool HYB, bool STEREO, int CH> WVB_DEV bool decode_word(BitReader &br,
         if (!held0 && (unsigned)t >= 16u) { // escape: 16 ones, then a zero and a gamma-coded count, or a 17th one = end of stream
             br.consume(16);
             nb = 0;
+            t = 0;
             if (br.getbit()) st = -1;
             else {
                 uint32_t v = 0;
                 if (!read_gamma(br, v)) st = -1;
-                t = (int)v + 16;
+                else t = (int)v + 16;
             }
         }
         br.consume(held0 ? 0 : nb);
         const int ones = held0 ? 0 : (t >> 1) + (w.hold == 1 ? 1 : 0);
         w.hold = held0 ? 0 : 2 - (t & 1);
 
-        if (st > 0) {
+        { // after a failed escape (st < 0) this still runs, on a harmless t = 0: the block's entropy state is dead by then
             if constexpr (HYB && CH == 0) update_error_limit<STEREO>(w, flags); // WordsUtils.cs:430-431
 
             uint32_t low, high; // WordsUtils.cs:433-475
