@@ -46,7 +46,7 @@ struct SharedColumn { // word i of this thread's column; [slot][thread] layout
     __device__ __forceinline__ int &operator()(int i) { return base[i * CTA_THREADS]; }
 };
 
-template <bool STEREO, bool HYB, bool GENFIX, class DEC, int MINB = 0>
+template <bool STEREO, bool HYB, bool GENFIX, class DEC, int MINB = 0, bool F16 = false>
 __global__ void __launch_bounds__(CTA_THREADS, MINB)
 k_decode_pcm(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ descs, const uint32_t *__restrict__ order,
              uint32_t count, uint8_t *__restrict__ out, int out_format, wvb_block_result *__restrict__ results)
@@ -56,7 +56,7 @@ k_decode_pcm(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ 
     const bool valid = i < count; // lanes past the end keep running (with no work): the decode loop is warp-synchronous
     const uint32_t bi = order[valid ? i : count - 1];
     SharedColumn SM{smem + threadIdx.x};
-    wvb::decode_block_pcm<STEREO, HYB, GENFIX, SharedColumn, DEC>(SM, in, descs[bi], out, out_format, &results[bi], valid);
+    wvb::decode_block_pcm<STEREO, HYB, GENFIX, SharedColumn, DEC, F16>(SM, in, descs[bi], out, out_format, &results[bi], valid);
 }
 
 using GenS = wvb::GenericDecorr<true>;
@@ -113,17 +113,17 @@ pcm_kernel_t pcm_kernel(int variant, uint32_t count = 0, int sm_count = 148)
     switch (variant) {
     case wvb::V_MONO: return k_decode_pcm<false, false, false, GenM>;
     case wvb::V_STEREO: return k_decode_pcm<true, false, false, GenS>;
+    case wvb::V_STEREO | wvb::V_F16: return k_decode_pcm<true, false, false, GenS, 0, true>;
     case wvb::V_MONO | wvb::V_FIXED: return k_decode_pcm<false, false, false, FixM>;
-    case wvb::V_STEREO | wvb::V_FIXED: {
+    case wvb::V_STEREO | wvb::V_FIXED: return k_decode_pcm<true, false, false, FixS>;
+    case wvb::V_STEREO | wvb::V_FIXED | wvb::V_F16: {
         // Two builds of the same kernel: 91 registers (5 CTAs/SM, no spills) and, compiled for 6 resident CTAs/SM, 80 registers
         // with ~50 B of spills.  The second wins once the launch no longer fits one wave of the first (measured on B200:
         // 200k blocks 114.5 -> 108.4 ms; 80k blocks 49.2 vs 52.7 ms).  WVB_FIXED_OCC overrides for experiments.
         static const int env_occ = getenv("WVB_FIXED_OCC") ? atoi(getenv("WVB_FIXED_OCC")) : -1;
         const int occ = env_occ >= 0 ? env_occ : (count > (uint32_t)sm_count * 5u * CTA_THREADS ? 6 : 0);
-        if (occ == 6) return k_decode_pcm<true, false, false, FixS, 6>;
-        if (occ == 7) return k_decode_pcm<true, false, false, FixS, 7>;
-        if (occ == 8) return k_decode_pcm<true, false, false, FixS, 8>;
-        return k_decode_pcm<true, false, false, FixS>;
+        if (occ == 6) return k_decode_pcm<true, false, false, FixS, 6, true>;
+        return k_decode_pcm<true, false, false, FixS, 0, true>;
     }
     case wvb::V_MONO | wvb::V_GENFIX: return k_decode_pcm<false, false, true, GenM>;
     case wvb::V_STEREO | wvb::V_GENFIX: return k_decode_pcm<true, false, true, GenS>;
@@ -143,7 +143,7 @@ int smem_class(int words)
 }
 
 // Sort blocks so that warps are homogeneous; emit one launch per (variant, smem class).
-void make_plan(const wvb_block_desc *descs, size_t n, std::vector<uint32_t> &order, std::vector<Launch> &launches)
+void make_plan(const wvb_block_desc *descs, size_t n, int fmt, std::vector<uint32_t> &order, std::vector<Launch> &launches)
 {
     order.resize(n);
     std::iota(order.begin(), order.end(), 0u);
@@ -151,6 +151,8 @@ void make_plan(const wvb_block_desc *descs, size_t n, std::vector<uint32_t> &ord
     for (size_t i = 0; i < n; i++) {
         const wvb_block_desc &d = descs[i];
         int v = wvb::variant_of(d);
+        // 16-bit interleaved stereo PCM gets its own launches: one aligned word store per frame, no byte-packing state
+        if ((v & ~wvb::V_FIXED) == wvb::V_STEREO && wvb::block_is_fast16(d, fmt == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : fmt)) v |= wvb::V_F16;
         int cls = v == wvb::V_DSD ? wvb::dsd_mode_class(d) : smem_class(d.smem_words);
         uint64_t clsbits = (uint64_t)(cls < 0 ? 1023 : cls) & 1023;
         // variant | class | term signature (16 bits) | inverted length (so long blocks start first)
@@ -263,10 +265,10 @@ static int validate_table(const wvb_block_desc *descs, size_t nblocks, size_t in
     return WVB_OK;
 }
 
-static int upload_table(wvb_batch *b, const wvb_block_desc *descs, size_t nblocks)
+static int upload_table(wvb_batch *b, const wvb_block_desc *descs, size_t nblocks, int fmt)
 {
     int rc;
-    make_plan(descs, nblocks, b->order, b->plan);
+    make_plan(descs, nblocks, fmt, b->order, b->plan);
     if ((rc = ensure(b->d_descs, b->d_descs_cap, nblocks + 1)) != WVB_OK) return rc;
     if ((rc = ensure(b->d_order, b->d_order_cap, nblocks + 1)) != WVB_OK) return rc;
     if (nblocks) {
@@ -386,7 +388,7 @@ static int decode_pipelined(wvb_batch *b, const uint8_t *in, size_t in_bytes, co
     {
         std::vector<uint32_t> tmp;
         for (size_t k = 0; k < segs.size(); k++) {
-            make_plan(descs + segs[k].first, segs[k].count, tmp, plans[k]);
+            make_plan(descs + segs[k].first, segs[k].count, fmt, tmp, plans[k]);
             for (size_t j = 0; j < tmp.size(); j++) b->order[segs[k].first + j] = (uint32_t)(tmp[j] + segs[k].first);
             for (Launch &L : plans[k]) L.first += (uint32_t)segs[k].first;
         }
@@ -438,7 +440,7 @@ int wvb_batch_prepare(wvb_batch *b, const wvb_block_desc *descs, size_t nblocks,
     b->prepared = false;
     int rc = validate_table(descs, nblocks, ~(size_t)0 >> 1, ~(size_t)0 >> 1, out_format);
     if (rc != WVB_OK) return rc;
-    if ((rc = upload_table(b, descs, nblocks)) != WVB_OK) return rc;
+    if ((rc = upload_table(b, descs, nblocks, out_format)) != WVB_OK) return rc;
     CUDA_TRY(cudaStreamSynchronize(b->stream));
     b->prepared_in_extent = b->prepared_out_extent = 0;
     for (size_t i = 0; i < nblocks; i++) {
@@ -498,7 +500,7 @@ int wvb_batch_decode(wvb_batch *b, const uint8_t *in, size_t in_bytes, const wvb
         if ((rc = ensure(b->d_results, b->d_results_cap, nblocks + 1)) != WVB_OK) return rc;
         dres = b->d_results;
     }
-    if (descs && (rc = upload_table(b, descs, nblocks)) != WVB_OK) return rc;
+    if (descs && (rc = upload_table(b, descs, nblocks, out_format)) != WVB_OK) return rc;
     CUDA_TRY(cudaEventRecord(b->ev[1], s));
 
     if ((rc = ensure_dsd_scratch(b, b->plan)) != WVB_OK) return rc;

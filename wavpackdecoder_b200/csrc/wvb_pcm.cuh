@@ -726,6 +726,46 @@ WVB_DEV void store_unit(uint8_t *q, int v, int unit, int add128)
     else q[0] = (uint8_t)(v + add128);
 }
 
+// Packs a block's contiguous output bytes into aligned 32-bit stores.  One store instruction of a warp touches 32
+// different output streams (32 sectors) whatever its width, so 24-bit stereo written byte by byte costs six such
+// instructions per frame and saturates the load/store path (ncu: L1TEX 71 % busy, decoder issue rate 27 %); packed, it is 1.5.
+// The first and last words of a block may be shared with its neighbours in the output: those are written bytewise.
+struct OutWriter {
+    uint8_t *p;   // 4-byte aligned address of the word being assembled
+    uint64_t acc; // bytes not stored yet, from bit 0
+    int fill;     // valid bits in acc (< 32 between calls)
+    int skip;     // leading bytes of the first word that belong to whatever precedes the block; 0 once that word is out
+
+    WVB_DEV void init(uint8_t *q)
+    {
+        const int mis = (int)((uintptr_t)q & 3);
+        p = q - mis;
+        acc = 0;
+        fill = 8 * mis;
+        skip = mis;
+    }
+    WVB_DEV void push(uint32_t v, int bits) // bits = 8, 16, 24 or 32; v already reduced to that width
+    {
+        acc |= (uint64_t)v << fill;
+        fill += bits;
+        if (fill >= 32) {
+            const uint32_t word = (uint32_t)acc;
+            if (skip) {
+                for (int k = skip; k < 4; ++k) p[k] = (uint8_t)(word >> (8 * k));
+                skip = 0;
+            } else
+                *(uint32_t *)p = word;
+            p += 4;
+            acc >>= 32;
+            fill -= 32;
+        }
+    }
+    WVB_DEV void finish() // the bytes of a last, partial word
+    {
+        for (int k = skip; k < (fill >> 3); ++k) p[k] = (uint8_t)(acc >> (8 * k));
+    }
+};
+
 // The reference decodes a block in caller-sized pieces (one unpack_samples call each).  piece_bounds() recovers the piece
 // [ps, pe) that contains sample t from the descriptor's chunk grid; it is evaluated only at piece events and on faults, so
 // the grid costs one register (the next event) in the sample loop.
@@ -746,7 +786,9 @@ template <bool STEREO> WVB_DEV uint32_t next_piece_event(uint32_t t, uint32_t ps
 
 // ---- the per-thread block decoder ------------------------------------------------------------
 // STEREO: two coded channels (neither MONO_FLAG nor FALSE_STEREO).  HYB: HYBRID_FLAG.  GENFIX: float / int32 / hybrid fixup.
-template <bool STEREO, bool HYB, bool GENFIX, class SMEM, class DEC = GenericDecorr<STEREO>>
+// F16: the block satisfies block_is_fast16 (wvb_plan.h; the planner gives such blocks their own launches); only meaningful
+// for STEREO && !GENFIX.
+template <bool STEREO, bool HYB, bool GENFIX, class SMEM, class DEC = GenericDecorr<STEREO>, bool F16 = false>
 WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc &D, uint8_t *out, int out_format, wvb_block_result *res,
                               bool valid = true)
 {
@@ -920,7 +962,12 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
     int mute_limit = (int)((1LL << ((flags >> 18) & 0x1f)) + 2); // UnpackUtils.cs:517
     if (flags & F_HYBRID) mute_limit *= 2;
     const bool joint = STEREO && (flags & F_JOINT);
-    const int fast16 = (!GENFIX && STEREO && out_format == WVB_OUT_PCM && unit == 2 && D.out_stride == 2 && D.out_ch_offset == 0) ? 1 : 0;
+    constexpr bool fast16 = F16 && STEREO && !GENFIX;
+    // the block's output is one contiguous byte run unless it is a channel pair inside wider frames (multichannel files)
+    const bool packed = !fast16 && D.out_stride == out_ch && D.out_ch_offset == 0;
+    const uint32_t unit_mask = unit == 4 ? 0xffffffffu : ((1u << (8 * unit)) - 1u);
+    OutWriter ow;
+    ow.init(op);
 
     // call/chunk grid: weights are cast to short at the end of every pass call, i.e. after the first 8 samples of a stereo
     // piece of >= 16 samples and at the end of the piece (UnpackUtils.cs:604-605,942-943,1152-1153,1239)
@@ -966,7 +1013,7 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
                 crc = crc * 3 + a;
                 if (STEREO) crc = crc * 3 + b;
                 if (!eof_fault) {
-                    if (fast16) {
+                    if constexpr (fast16) {
                         *(uint32_t *)op = ((uint32_t)shl32(a, fx.shift) & 0xffffu) | ((uint32_t)shl32(b, fx.shift) << 16);
                     } else {
                         int va, vb = 0;
@@ -977,8 +1024,13 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
                             va = shl32(a, fx.shift);
                             if (STEREO) vb = shl32(b, fx.shift);
                         }
-                        store_unit(op, va, unit, add128);
-                        if (out_ch == 2) store_unit(op + unit, STEREO ? vb : va, unit, add128); // FALSE_STEREO duplicates (UnpackUtils.cs:668-680)
+                        if (packed) {
+                            ow.push((uint32_t)(va + add128) & unit_mask, 8 * unit);
+                            if (out_ch == 2) ow.push((uint32_t)((STEREO ? vb : va) + add128) & unit_mask, 8 * unit);
+                        } else {
+                            store_unit(op, va, unit, add128);
+                            if (out_ch == 2) store_unit(op + unit, STEREO ? vb : va, unit, add128); // FALSE_STEREO duplicates (UnpackUtils.cs:668-680)
+                        }
                     }
                     op += frame_bytes;
                 } else { // the modelled remainder of the chunk ends with the piece
@@ -994,6 +1046,8 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
             }
         }
     }
+
+    if (packed) ow.finish();
 
     if (fault) { // mute from the start of the caller chunk that contains the fault (UnpackUtils.cs:649-664, App. E-10)
         rflags |= WVB_RF_MUTED;

@@ -7,7 +7,7 @@
 namespace wvb {
 
 // kernel variants of the PCM path
-enum { V_MONO = 0, V_STEREO = 1, V_GENFIX = 2, V_HYBRID = 4, V_DSD = 8, V_FIXED = 16, V_COUNT = 32 };
+enum { V_MONO = 0, V_STEREO = 1, V_GENFIX = 2, V_HYBRID = 4, V_DSD = 8, V_FIXED = 16, V_F16 = 32, V_COUNT = 64 };
 
 // FNV-1a over the term list in DECODER order, as wvb_index computes wvb_block_desc.terms_sig
 constexpr uint32_t terms_hash(const int *t, int n)
@@ -25,6 +25,15 @@ constexpr int kFixedStereo[] = {WVB_FIXED_STEREO_TERMS};
 constexpr int kFixedMono[] = {WVB_FIXED_MONO_TERMS};
 constexpr uint32_t kFixedStereoSig = terms_hash(kFixedStereo, 5);
 constexpr uint32_t kFixedMonoSig = terms_hash(kFixedMono, 4);
+
+// 16-bit interleaved stereo PCM, the bench case: one aligned 32-bit store per frame, no byte packing state to carry
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline bool block_is_fast16(const wvb_block_desc &D, int out_format)
+{
+    return out_format == WVB_OUT_PCM && D.out_bps == 2 && D.out_stride == 2 && D.out_ch_offset == 0;
+}
 
 inline int variant_of(const wvb_block_desc &d)
 {
