@@ -390,8 +390,17 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic.get("dram_bytes_per_launch") if traffic and traffic.get("blocks_per_launch") == cp.nblocks else None,
                 "traffic_source": traffic.get("source") if traffic else None, "peak_kind": peak_kind,
-                "kernel": "k_decode_pcm<stereo,lossless,FixedDecorr<-2,3,2,18,18>>", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": int(algo_bytes),
+                "kernel": "k_decode_pcm<stereo,lossless,FixedDecorr<-2,3,2,18,18>,F16>", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": int(algo_bytes),
                 "bytes_per_sample": algo_bytes / total_samples}
+    # What actually binds the kernel (explanatory, the contract's bound stays "hbm"): warp-instruction issue.  Instructions per
+    # launch come from the same ncu capture as `traffic`; the rate is this run's, against SMs x 4 schedulers x the sampled clock.
+    if traffic and traffic.get("blocks_per_launch") == cp.nblocks and traffic.get("warp_instructions_per_launch") and clk.get("sm_mhz"):
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        issue_peak = sms * 4 * clk["sm_mhz"] * 1e6
+        issue_rate = traffic["warp_instructions_per_launch"] / (k_ms * 1e-3)
+        roofline["issue"] = {"warp_instructions_per_launch": traffic["warp_instructions_per_launch"], "achieved": issue_rate, "peak": issue_peak,
+                             "unit": "warp-inst/s", "frac": issue_rate / issue_peak,
+                             "warp_instructions_per_32_samples": traffic["warp_instructions_per_launch"] / total_samples * 32}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
