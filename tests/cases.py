@@ -76,6 +76,14 @@ PCM_CASES = [
     ("ff_list_one_term", 0, 4096, dict(terms=[1])),
     ("ff_list_mono", 0, 4096, dict(channels=1, terms=[18, 17, 3, 2, 1])),
     ("ff_list_false_stereo", 0, 4096, dict(false_stereo=1, terms=[17, 18, 18, 1, 2], seconds=1.2)),
+    # odd block lengths: block outputs start at byte offsets that are not multiples of four (packed output writer head/tail)
+    ("8bit_mono_odd_blocks", 0, 4096, dict(bits=8, channels=1, block_samples=1001, seconds=0.25)),
+    ("8bit_stereo_odd_blocks", 0, 4096, dict(bits=8, block_samples=1001, seconds=0.25)),
+    ("16bit_mono_odd_blocks", 0, 4096, dict(channels=1, block_samples=1001, seconds=0.25)),
+    ("24bit_mono_odd_blocks", 0, 4096, dict(bits=24, channels=1, block_samples=1001, seconds=0.25)),
+    ("24bit_stereo_odd_blocks", 0, 4096, dict(bits=24, block_samples=1001, seconds=0.25)),
+    ("24bit_mono_tiny_blocks", 0, 4096, dict(bits=24, channels=1, block_samples=1, seconds=0.002)),
+    ("8bit_mono_tiny_blocks", 0, 3, dict(bits=8, channels=1, block_samples=3, seconds=0.003)),
     ("list_six_terms", 0, 4096, dict(terms=[18, 18, 2, 17, 3, 1])),
     ("list_term4", 0, 4096, dict(terms=[18, 4, 2])),
 ]

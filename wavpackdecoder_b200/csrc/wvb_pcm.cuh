@@ -129,7 +129,8 @@ struct BitReader {
         // on the prefetch issued just before it.
         // (the ballot's result feeds a condition that never holds, only so that the read is not optimised away)
         uint32_t seen;
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\tvote.sync.ballot.b32 %0, p, 0xffffffff;\n\t}" : "=r"(seen) : "r"(w0 | w1 | nw));
+        // (active mask, not the full one: the WVX reader is set up under per-lane conditions)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\tvote.sync.ballot.b32 %0, p, %2;\n\t}" : "=r"(seen) : "r"(w0 | w1 | nw), "r"(__activemask()));
         if (seen == 0x5a5a5a5au && len == 0xffffffffu) ++pos;
 #endif
     }
