@@ -275,6 +275,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device; libwvb has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner / debug output (it defaults to stdout) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
