@@ -335,7 +335,17 @@ static int decode_pipelined(wvb_batch *b, const uint8_t *in, size_t in_bytes, co
     if (nseg > 16) nseg = 16;
     struct Seg { size_t first, count; uint64_t in_lo, in_hi, out_lo, out_hi; };
     std::vector<Seg> segs;
-    const uint64_t total = in_bytes + out_bytes, per = total / nseg + 1;
+    // Segment sizes ramp up from a small first segment and down to a small last one (weights 1,2,3,4,...,4,3,2,1): the
+    // first bytes can start their way back after the decode of a short segment (a block is a serial chain of ~30-50 ms
+    // whatever the batch size, so that first decode cannot be hidden), and little is left to copy after the last kernel.
+    std::vector<uint64_t> quota(nseg);
+    {
+        uint64_t wsum = 0;
+        std::vector<uint64_t> wt(nseg);
+        for (size_t k = 0; k < nseg; k++) { wt[k] = std::min<uint64_t>(std::min<uint64_t>(k + 1, nseg - k), 4); wsum += wt[k]; }
+        const uint64_t total = in_bytes + out_bytes;
+        for (size_t k = 0; k < nseg; k++) quota[k] = total / wsum * wt[k] + 1;
+    }
     uint64_t acc = 0;
     Seg cur{0, 0, ~0ull, 0, ~0ull, 0};
     for (size_t i = 0; i < nblocks; i++) {
@@ -347,7 +357,7 @@ static int decode_pipelined(wvb_batch *b, const uint8_t *in, size_t in_bytes, co
         cur.out_lo = std::min<uint64_t>(cur.out_lo, std::min(olo, d.out_offset)); cur.out_hi = std::max(cur.out_hi, ohi);
         cur.count++;
         acc += d.in_bytes + (ohi - d.out_offset);
-        if (acc >= per || i + 1 == nblocks) {
+        if (acc >= quota[std::min(segs.size(), nseg - 1)] || i + 1 == nblocks) {
             segs.push_back(cur);
             cur = Seg{i + 1, 0, ~0ull, 0, ~0ull, 0};
             acc = 0;
