@@ -213,6 +213,18 @@ int wvb_batch_timing(wvb_batch *b, float *kernel_ms, float *h2d_ms, float *d2h_m
 /* the batch's cudaStream_t, for callers that want to order their own work after it */
 void *wvb_batch_stream(wvb_batch *b);
 
+/* ---- integrity (beyond the reference, which ignores ID_MD5_CHECKSUM, MetadataUtils.cs:187-191) ----
+ * MD5 (RFC 1321) of n byte ranges of a decoded output slab, computed on the device: digests[16*i..] = MD5 of
+ * slab[offsets[i] .. offsets[i]+lengths[i]).  device_out: the slab a WVB_OUT_DEVICE decode wrote (out_bytes = its
+ * size), or NULL for the batch's own device copy of the last host-buffer decode.  offsets/lengths/digests are host
+ * pointers.  With one range per file (its PCM) the result compares directly with the file's stored MD5, and a
+ * verify-only pass never moves PCM over PCIe. */
+int wvb_batch_md5(wvb_batch *b, const void *device_out, size_t out_bytes, const uint64_t *offsets, const uint64_t *lengths, size_t n,
+                  uint8_t *digests);
+/* The MD5 a .wv file stores for its source audio (ID_MD5_CHECKSUM, Defines.cs:77), searched in every block's
+ * metadata.  Returns 1 and fills md5 if present, 0 if not. */
+int wvb_stored_md5(const uint8_t *file, size_t len, uint8_t md5[16]);
+
 /* pinned host memory helpers for hosts without their own allocator (C# shim) */
 void *wvb_host_alloc(size_t bytes);
 void wvb_host_free(void *p);

@@ -2137,3 +2137,95 @@ long rd_decode_file_pcm(const uint8_t *file, size_t len, uint32_t open_flags, lo
     rd_close(c);
     return total;
 }
+
+/* ---- WvDemo.Main restated (WvDemo.cs:15-174): the bytes it writes to <input>.<ext> and its exit code ----------
+ * out receives the output file.  Exit codes as the demo returns them: 0 ok; 1 open error, exception while
+ * writing (incl. the DivideByZeroException of `total_unpacked_samples % loop_samples` when the file has fewer
+ * than 100 * SAMPLE_BUFFER_SIZE samples, WvDemo.cs:113,136 -- raised after the first chunk has been written),
+ * wrong sample count, or CRC errors.  Returns the number of bytes written, or -1 if out is too small. */
+#define RD_SAMPLE_BUFFER_SIZE 4096 /* Defines.cs:18 */
+static void le32(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
+static void le16(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
+
+long rd_wvdemo(const uint8_t *file, size_t len, uint8_t *out, size_t cap, int *exit_code)
+{
+    size_t at = 0;
+    int rc = 0;
+    long total_unpacked = 0;
+    rd_context *c = rd_open(file, len, 0); /* WvDemo.cs:28 */
+    if (rd_get_error_message(c)) { /* WvDemo.cs:41-46 */
+        rd_close(c);
+        if (exit_code) *exit_code = 1;
+        return 0;
+    }
+    const int nch = rd_get_reduced_channels(c);       /* WvDemo.cs:48-53 */
+    const int bits = rd_get_bits_per_sample(c);
+    const int byteps = rd_get_bytes_per_sample(c);
+    const int block_align = byteps * nch;
+    const long total_samples = rd_get_num_samples(c, 1);
+    const long sample_rate = rd_get_sample_rate(c);
+
+    long hlen = 0;
+    const uint8_t *hdr = rd_get_header(c, &hlen); /* WvDemo.cs:74-77: stored header unless the file is float */
+    if (hdr && !rd_get_is_float(c)) {
+        if (at + (size_t)hlen > cap) { rd_close(c); return -1; }
+        memcpy(out + at, hdr, (size_t)hlen);
+        at += (size_t)hlen;
+    } else { /* WvDemo.cs:78-105: RIFF(12) + "fmt "(8) + WaveHeader(16) + "data"(8) */
+        if (at + 44 > cap) { rd_close(c); return -1; }
+        uint8_t *h = out + at;
+        const uint32_t data_bytes = (uint32_t)((int64_t)total_samples * block_align);
+        memcpy(h, "RIFF", 4);
+        le32(h + 4, (uint32_t)(data_bytes + 2 * 8 + 16) + 4u); /* RiffChunkHeader.cs:16 adds 4 for "WAVE" */
+        memcpy(h + 8, "WAVE", 4);
+        memcpy(h + 12, "fmt ", 4);
+        le32(h + 16, 16);
+        le16(h + 20, 1);                                           /* FormatTag */
+        le16(h + 22, (uint32_t)nch & 0xffff);                      /* (ushort)num_channels */
+        le32(h + 24, (uint32_t)sample_rate);
+        le32(h + 28, (uint32_t)((int64_t)sample_rate * block_align)); /* BytesPerSecond */
+        le16(h + 32, (uint32_t)block_align & 0xffff);
+        le16(h + 34, (uint32_t)bits & 0xffff);
+        memcpy(h + 36, "data", 4);
+        le32(h + 40, data_bytes);
+        at += 44;
+    }
+
+    const long samples_unpack = RD_SAMPLE_BUFFER_SIZE;                                  /* WvDemo.cs:111 */
+    const long loop_samples = total_samples / 100 / samples_unpack * samples_unpack;   /* WvDemo.cs:113 */
+    int32_t *tmp = (int32_t *)malloc(sizeof(int32_t) * (size_t)samples_unpack * (size_t)(nch > 0 ? nch : 1));
+    int threw = 0;
+    for (;;) { /* WvDemo.cs:118-141 */
+        long n = rd_unpack_samples(c, tmp, samples_unpack * nch, samples_unpack);
+        if (n < 0) { threw = 1; break; } /* an exception out of the decoder lands in the catch-all, WvDemo.cs:148 */
+        total_unpacked += n;
+        if (n > 0) {
+            const size_t bytes = (size_t)n * (size_t)block_align;
+            if (at + bytes > cap) { free(tmp); rd_close(c); return -1; }
+            /* pcm_buffer has samples_unpack * block_align bytes; dsd defaults to false (WvDemo.cs:125) */
+            if (!rd_format_samples(tmp, n * nch, byteps, out + at, (long)(samples_unpack * block_align), 0, 0)) break;
+            at += bytes;
+        }
+        if (loop_samples == 0) { threw = 1; break; } /* DivideByZeroException, WvDemo.cs:136 */
+        if (n == 0) break;
+    }
+    free(tmp);
+    if (threw) { /* WvDemo.cs:148-153: the using block closes the file with what was written so far */
+        rd_close(c);
+        if (exit_code) *exit_code = 1;
+        return (long)at;
+    }
+    long tlen = 0;
+    const uint8_t *trl = rd_get_trailer(c, &tlen); /* WvDemo.cs:143-145 */
+    if (trl) {
+        if (at + (size_t)tlen > cap) { rd_close(c); return -1; }
+        memcpy(out + at, trl, (size_t)tlen);
+        at += (size_t)tlen;
+    }
+    const long num_samples = rd_get_num_samples(c, 0); /* WvDemo.cs:157-162 */
+    if (num_samples != -1 && total_unpacked != num_samples) rc = 1;
+    else if (rd_get_num_errors(c) > 0) rc = 1; /* WvDemo.cs:164-169 */
+    rd_close(c);
+    if (exit_code) *exit_code = rc;
+    return (long)at;
+}

@@ -84,6 +84,10 @@ int rd_dbg_check_crc_error(rd_context *c);
 long rd_decode_file_pcm(const uint8_t *file, size_t len, uint32_t open_flags, long chunk_samples,
                         uint8_t *pcm, size_t pcm_cap, size_t *pcm_len, long *crc_errors);
 
+/* WvDemo.Main restated (WvDemo.cs:15-174): writes the bytes the demo writes to its output file into out and its
+ * process exit code into *exit_code.  Returns the byte count, -1 if cap is too small. */
+long rd_wvdemo(const uint8_t *file, size_t len, uint8_t *out, size_t cap, int *exit_code);
+
 #ifdef __cplusplus
 }
 #endif

@@ -149,6 +149,8 @@ def refdec():
         lib.rd_decode_file_pcm.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_long, C.c_void_p, C.c_size_t,
                                            C.POINTER(C.c_size_t), C.POINTER(C.c_long)]
         lib.rd_decode_file_pcm.restype = C.c_long
+        lib.rd_wvdemo.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]
+        lib.rd_wvdemo.restype = C.c_long
         lib.rd_dbg_table.argtypes = [C.c_int, C.c_int]
         _ref = lib
     return _ref
@@ -304,3 +306,17 @@ def emul_decode_file(data, open_flags=0, chunk=4096, out_format=0):
     if out_format == 0:
         out = out.view(np.int32)
     return out, info, [res[i] for i in range(n)], [descs[i] for i in range(n)]
+
+
+def oracle_wvdemo(data):
+    """WvDemo.Main restated by the oracle: (output file bytes, exit code)."""
+    lib = refdec()
+    buf = np.frombuffer(data, dtype=np.uint8)
+    cap = 64 + buf.size * 40 + (1 << 16)
+    while True:
+        out = np.zeros(cap, dtype=np.uint8)
+        code = C.c_int(-1)
+        n = lib.rd_wvdemo(buf.ctypes.data, buf.size, out.ctypes.data, cap, C.byref(code))
+        if n >= 0:
+            return out[:n].tobytes(), code.value
+        cap *= 4

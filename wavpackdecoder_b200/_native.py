@@ -57,7 +57,7 @@ assert C.sizeof(BlockResult) == 16
 EXPORTS = [
     "wvb_abi_version", "wvb_last_error", "wvb_device_count", "wvb_index", "wvb_index_many", "wvb_rebase", "wvb_frame_bytes",
     "wvb_batch_create", "wvb_batch_destroy", "wvb_batch_prepare", "wvb_batch_decode", "wvb_batch_wait", "wvb_batch_timing", "wvb_batch_stream",
-    "wvb_host_alloc", "wvb_host_free",
+    "wvb_host_alloc", "wvb_host_free", "wvb_batch_md5", "wvb_stored_md5",
 ]
 
 
@@ -74,6 +74,8 @@ def declare_index_api(lib):
     lib.wvb_rebase.restype = None
     lib.wvb_frame_bytes.argtypes = [C.POINTER(BlockDesc), C.c_int]
     lib.wvb_frame_bytes.restype = C.c_uint32
+    lib.wvb_stored_md5.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.wvb_stored_md5.restype = C.c_int
     return lib
 
 
@@ -109,6 +111,8 @@ def load():
     lib.wvb_batch_timing.restype = C.c_int
     lib.wvb_batch_stream.argtypes = [C.c_void_p]
     lib.wvb_batch_stream.restype = C.c_void_p
+    lib.wvb_batch_md5.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.wvb_batch_md5.restype = C.c_int
     lib.wvb_host_alloc.argtypes = [C.c_size_t]
     lib.wvb_host_alloc.restype = C.c_void_p
     lib.wvb_host_free.argtypes = [C.c_void_p]

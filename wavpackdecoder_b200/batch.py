@@ -124,6 +124,16 @@ class BatchDecoder:
         _check(self.lib, self.lib.wvb_batch_timing(self.h, C.byref(k), C.byref(h), C.byref(d), C.byref(n)), "wvb_batch_timing")
         return dict(kernel_ms=k.value, h2d_ms=h.value, d2h_ms=d.value, launches=n.value)
 
+    def md5_ranges(self, offsets, lengths, out_bytes, device_out=None):
+        """MD5 of byte ranges of the decoded output, computed on the device (wvb_batch_md5).  device_out: device pointer of
+        a WVB_OUT_DEVICE decode, or None for the batch's own copy of the last host-buffer decode.  Returns (n, 16) uint8."""
+        offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+        lens = np.ascontiguousarray(lengths, dtype=np.uint64)
+        dig = np.zeros((offs.size, 16), dtype=np.uint8)
+        rc = self.lib.wvb_batch_md5(self.h, device_out, out_bytes, offs.ctypes.data, lens.ctypes.data, offs.size, dig.ctypes.data)
+        _check(self.lib, rc, "wvb_batch_md5")
+        return dig
+
     def decode_corpus(self, corpus, out=None):
         """Host-buffer decode of a whole Corpus.  Returns (out uint8 array, results array)."""
         if out is None:
@@ -147,4 +157,44 @@ def decode_files(files, open_flags=0, chunk_samples=4096, out_format=N.OUT_INT32
         f, c = int(corpus.first[i]), int(corpus.count[i])
         errs = sum(1 for k in range(f, f + c) if results[k].rflags & N.RF_CRC_ERROR)
         res.append((corpus.file_output(out, i).copy(), errs, corpus.infos[i], [results[k] for k in range(f, f + c)]))
+    return res
+
+
+def stored_md5(data):
+    """The MD5 a .wv file stores for its source audio (ID_MD5_CHECKSUM), or None."""
+    lib = N.load()
+    buf = np.frombuffer(data, dtype=np.uint8)
+    md5 = np.zeros(16, dtype=np.uint8)
+    return md5.tobytes() if lib.wvb_stored_md5(buf.ctypes.data, buf.size, md5.ctypes.data) else None
+
+
+def verify_files(files, device=0):
+    """Decode a list of .wv byte strings on the GPU and check each file against its stored MD5 without bringing the PCM
+    back: the output slab stays in device memory, only 16 bytes per file and the per-block results return.
+    Returns a list of dicts: md5 (hex of the decoded PCM), stored (hex or None), match (True/False/None when the file
+    stores no MD5), crc_errors, error (open error message or None)."""
+    import torch
+    corpus = Corpus.from_files(files, open_flags=0, chunk_samples=4096, out_format=N.OUT_PCM)
+    dev = torch.device("cuda", device)
+    d_out = torch.empty(corpus.out_bytes + 64, dtype=torch.uint8, device=dev)
+    results = (N.BlockResult * max(corpus.nblocks, 1))()
+    dec = BatchDecoder(device)
+    try:
+        if corpus.nblocks:
+            dec.decode(corpus.slab.ctypes.data, corpus.slab.size, corpus.descs, corpus.nblocks, d_out.data_ptr(), corpus.out_bytes,
+                       N.OUT_PCM, N.OUT_DEVICE, results)
+        lens = np.array([int(corpus.infos[i].indexed_samples) * corpus.file_channels(i) * int(corpus.infos[i].bytes_per_sample)
+                         for i in range(corpus.nfiles)], dtype=np.uint64)
+        dig = dec.md5_ranges(corpus.file_out_offset, lens, corpus.out_bytes, d_out.data_ptr())
+    finally:
+        dec.close()
+    res = []
+    for i in range(corpus.nfiles):
+        info = corpus.infos[i]
+        msg = bytes(info.error_message).split(b"\0", 1)[0].decode() or None
+        f, c = int(corpus.first[i]), int(corpus.count[i])
+        st = stored_md5(files[i])
+        got = dig[i].tobytes()
+        res.append(dict(md5=got.hex(), stored=st.hex() if st else None, match=None if (st is None or msg) else st == got,
+                        crc_errors=sum(1 for k in range(f, f + c) if results[k].rflags & N.RF_CRC_ERROR), error=msg))
     return res

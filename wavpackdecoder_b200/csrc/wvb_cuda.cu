@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "wvb_dsd.cuh"
+#include "wvb_md5.cuh"
 #include "wvb_pcm.cuh"
 #include "wvb_plan.h"
 
@@ -72,6 +73,8 @@ struct wvb_batch {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // h2d0,h2d1(k0),k1,d2h1
     uint8_t *d_in = nullptr; size_t d_in_cap = 0;
     uint8_t *d_out = nullptr; size_t d_out_cap = 0;
+    uint64_t *d_md5_ranges = nullptr; size_t d_md5_ranges_cap = 0;
+    uint8_t *d_md5_out = nullptr; size_t d_md5_out_cap = 0;
     wvb_block_desc *d_descs = nullptr; size_t d_descs_cap = 0;
     uint32_t *d_order = nullptr; size_t d_order_cap = 0;
     wvb_block_result *d_results = nullptr; size_t d_results_cap = 0;
@@ -214,6 +217,7 @@ void wvb_batch_destroy(wvb_batch *b)
     if (!b) return;
     cudaSetDevice(b->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
+    cudaFree(b->d_md5_ranges); cudaFree(b->d_md5_out);
     cudaFree(b->d_in); cudaFree(b->d_out); cudaFree(b->d_descs); cudaFree(b->d_order); cudaFree(b->d_results);
     cudaFree(b->d_scratch); cudaFree(b->d_scratch_meta);
     for (auto &e : b->ev) if (e) cudaEventDestroy(e);
@@ -248,6 +252,34 @@ int wvb_batch_timing(wvb_batch *b, float *kernel_ms, float *h2d_ms, float *d2h_m
     if (kernel_ms) { CUDA_TRY(cudaEventElapsedTime(&v, b->ev[1], b->ev[2])); *kernel_ms = v; }
     if (d2h_ms) { CUDA_TRY(cudaEventElapsedTime(&v, b->ev[2], b->ev[3])); *d2h_ms = v; }
     if (launches) *launches = b->launches;
+    return WVB_OK;
+}
+
+int wvb_batch_md5(wvb_batch *b, const void *device_out, size_t out_bytes, const uint64_t *offsets, const uint64_t *lengths, size_t n, uint8_t *digests)
+{
+    if (!b || !offsets || !lengths || !digests) return WVB_E_ARG;
+    if (n == 0) return WVB_OK;
+    if (n > 0xfffffff0ull) return WVB_E_ARG;
+    CUDA_TRY(cudaSetDevice(b->device));
+    const uint8_t *src = (const uint8_t *)device_out;
+    if (!src) { // the batch's own copy of the last host-buffer decode
+        src = b->d_out;
+        if (!src || out_bytes > b->d_out_cap) return set_error(WVB_E_ARG, "wvb_batch_md5: no decoded output of that size is resident in the batch");
+    }
+    for (size_t i = 0; i < n; i++)
+        if (offsets[i] > out_bytes || lengths[i] > out_bytes - offsets[i]) return set_error(WVB_E_ARG, "wvb_batch_md5: range outside the output slab");
+    int rc;
+    if ((rc = ensure(b->d_md5_ranges, b->d_md5_ranges_cap, 2 * n)) != WVB_OK) return rc;
+    if ((rc = ensure(b->d_md5_out, b->d_md5_out_cap, 16 * n)) != WVB_OK) return rc;
+    cudaStream_t s = b->stream;
+    CUDA_TRY(cudaMemcpyAsync(b->d_md5_ranges, offsets, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(b->d_md5_ranges + n, lengths, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    wvb::k_md5_ranges<<<(unsigned)((n + wvb::MD5_THREADS - 1) / wvb::MD5_THREADS), wvb::MD5_THREADS, 0, s>>>(src, b->d_md5_ranges, b->d_md5_ranges + n, (uint32_t)n,
+                                                                                                            b->d_md5_out);
+    CUDA_TRY(cudaGetLastError());
+    b->launches++;
+    CUDA_TRY(cudaMemcpyAsync(digests, b->d_md5_out, 16 * n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
     return WVB_OK;
 }
 

@@ -622,6 +622,41 @@ int wvb_index(const uint8_t *file, size_t len, uint32_t open_flags, uint32_t chu
     return WVB_OK;
 }
 
+// ID_MD5_CHECKSUM (Defines.cs:77) lookup: a plain walk over every block's sub-blocks (TLV layout: MetadataUtils.cs:25-82),
+// independent of the reference's read order (the reference never looks at this id).
+int wvb_stored_md5(const uint8_t *file, size_t len, uint8_t md5[16])
+{
+    if (!file || !md5) return 0;
+    size_t pos = 0;
+    while (pos + 32 <= len) {
+        if (memcmp(file + pos, "wvpk", 4) != 0) { pos++; continue; }
+        const uint32_t ck = (uint32_t)file[pos + 4] | ((uint32_t)file[pos + 5] << 8) | ((uint32_t)file[pos + 6] << 16) | ((uint32_t)file[pos + 7] << 24);
+        if (ck < 24 || ck >= 0x100000u || (ck & 1) || pos + 8 + (size_t)ck > len) { pos++; continue; }
+        size_t at = pos + 32;
+        const size_t end = pos + 8 + ck;
+        while (at + 2 <= end) {
+            const uint8_t id = file[at];
+            size_t words = file[at + 1];
+            size_t hdr = 2;
+            if (id & 0x80) {
+                if (at + 4 > end) break;
+                words |= ((size_t)file[at + 2] << 8) | ((size_t)file[at + 3] << 16);
+                hdr = 4;
+            }
+            const size_t padded = words * 2;
+            if (at + hdr + padded > end) break;
+            const size_t actual = (id & 0x40) ? (padded ? padded - 1 : 0) : padded;
+            if ((id & 0x3f) == 0x26 && actual == 16) {
+                memcpy(md5, file + at + hdr, 16);
+                return 1;
+            }
+            at += hdr + padded;
+        }
+        pos = end;
+    }
+    return 0;
+}
+
 uint32_t wvb_frame_bytes(const wvb_block_desc *b, int out_format)
 {
     uint32_t unit = out_format == WVB_OUT_INT32 ? 4u : b->out_bps;

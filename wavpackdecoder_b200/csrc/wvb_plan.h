@@ -26,13 +26,14 @@ constexpr int kFixedMono[] = {WVB_FIXED_MONO_TERMS};
 constexpr uint32_t kFixedStereoSig = terms_hash(kFixedStereo, 5);
 constexpr uint32_t kFixedMonoSig = terms_hash(kFixedMono, 4);
 
-// 16-bit interleaved stereo PCM, the bench case: one aligned 32-bit store per frame, no byte packing state to carry
+// 16-bit interleaved stereo PCM at a 4-byte aligned slab offset, the bench case: one aligned 32-bit store per frame, no
+// byte packing state to carry (a caller-rebased table with odd offsets goes through the packed writer instead)
 #ifdef __CUDACC__
 __host__ __device__
 #endif
 inline bool block_is_fast16(const wvb_block_desc &D, int out_format)
 {
-    return out_format == WVB_OUT_PCM && D.out_bps == 2 && D.out_stride == 2 && D.out_ch_offset == 0;
+    return out_format == WVB_OUT_PCM && D.out_bps == 2 && D.out_stride == 2 && D.out_ch_offset == 0 && (D.out_offset & 3u) == 0;
 }
 
 inline int variant_of(const wvb_block_desc &d)

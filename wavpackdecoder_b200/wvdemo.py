@@ -1,0 +1,120 @@
+"""WvDemo (WvDemo.cs:15-174) on the batch decoder: .wv files in, the bytes the demo writes to <name>.<ext> out.
+
+SURVEY.md section 8f row 3 (container writer): the stored RIFF/alt header is passed through (or the 44-byte WAV header
+of WvDemo.cs:78-105 is synthesised), the PCM is decoded by the GPU *in place* between header and trailer -- every
+file's blocks are rebased so that the kernels write straight into the finished container -- and the stored trailer is
+appended.  Host work is the index pass and a few dozen header bytes per file; no PCM is touched on the host.
+
+This is plumbing over libwvb.so; like the rest of the package it has no CPU decode path.
+"""
+import struct
+
+import numpy as np
+
+from . import _native as N
+from . import wavpack_utils as W
+from .batch import BatchDecoder, Corpus
+
+SAMPLE_BUFFER_SIZE = W.SAMPLE_BUFFER_SIZE  # Defines.cs:18: WvDemo unpacks in chunks of this many samples
+
+
+def wave_header(total_samples, num_channels, sample_rate, bits, byteps):
+    """WvDemo.cs:78-105 with RiffChunkHeader.cs / ChunkHeader.cs / WaveHeader.cs: 12 + 8 + 16 + 8 bytes, fields
+    truncated to their C# types (uint / ushort casts)."""
+    block_align = byteps * num_channels
+    data_bytes = (total_samples * block_align) & 0xffffffff
+    riff_size = ((data_bytes + 2 * 8 + 16) & 0xffffffff) + 4 & 0xffffffff  # RiffChunkHeader.cs:16 adds the 4 of "WAVE"
+    return (b"RIFF" + struct.pack("<I", riff_size) + b"WAVE" + b"fmt " + struct.pack("<I", 16) +
+            struct.pack("<HHIIHH", 1, num_channels & 0xffff, sample_rate & 0xffffffff, (sample_rate * block_align) & 0xffffffff,
+                        block_align & 0xffff, bits & 0xffff) +
+            b"data" + struct.pack("<I", data_bytes))
+
+
+def _context(corpus, i):
+    """A WavpackContext over file i of an indexed corpus, for the getters of wavpack_utils (no second index pass)."""
+    wpc = W.WavpackContext()
+    o, n = int(corpus.offsets[i]), int(corpus.sizes[i])
+    wpc.data = corpus.slab[o:o + n]
+    wpc.info = corpus.infos[i]
+    msg = bytes(wpc.info.error_message).split(b"\0", 1)[0]
+    wpc.error_message = msg.decode() if msg else None
+    return wpc
+
+
+def unpack_files(files, device=0, reference_quirks=True):
+    """Decode a list of .wv byte strings the way WvDemo.Main does.  Returns a list of (output file bytes, exit code).
+
+    reference_quirks: files with fewer than 100 * SAMPLE_BUFFER_SIZE (409 600) samples, or of unknown length, make the reference demo throw
+    DivideByZeroException at its progress print (`total_unpacked_samples % loop_samples`, WvDemo.cs:113,136) after the
+    first chunk has been written: it leaves header + first chunk on disk and exits 1.  True reproduces that; False
+    writes the complete file."""
+    corpus = Corpus.from_files(files, open_flags=0, chunk_samples=SAMPLE_BUFFER_SIZE, out_format=N.OUT_PCM)
+    nfiles = corpus.nfiles
+    ctxs = [_context(corpus, i) for i in range(nfiles)]
+    heads, tails, pcm_bytes, ok = [], [], [], []
+    for i, wpc in enumerate(ctxs):
+        if W.WavpackGetErrorMessage(wpc):  # WvDemo.cs:41-46: no output file at all
+            heads.append(b""); tails.append(b""); pcm_bytes.append(0); ok.append(False)
+            continue
+        nch = W.WavpackGetReducedChannels(wpc)
+        byteps = W.WavpackGetBytesPerSample(wpc)
+        header = W.WavpackGetHeader(wpc)
+        if header is not None and not W.WavpackGetIsFloat(wpc):  # WvDemo.cs:76-77
+            heads.append(header)
+        else:
+            heads.append(wave_header(W.WavpackGetNumSamples(wpc, True), nch, W.WavpackGetSampleRate(wpc),
+                                     W.WavpackGetBitsPerSample(wpc), byteps))
+        trailer = W.WavpackGetTrailer(wpc)  # WvDemo.cs:143-145
+        tails.append(trailer if trailer is not None else b"")
+        pcm_bytes.append(int(wpc.info.indexed_samples) * nch * byteps)
+        ok.append(True)
+
+    # container layout: every file's PCM starts 64-byte aligned (the 16-bit stereo kernel stores aligned words), its header
+    # immediately before and its trailer immediately after
+    pcm_start = np.zeros(nfiles, dtype=np.uint64)
+    cursor = 0
+    for i in range(nfiles):
+        start = (cursor + len(heads[i]) + 63) & ~63
+        pcm_start[i] = start
+        cursor = start + pcm_bytes[i] + len(tails[i])
+    total = cursor
+    if corpus.nblocks:
+        delta = (pcm_start - corpus.file_out_offset).astype(np.uint64)  # modular: a negative shift wraps correctly
+        table = np.frombuffer(corpus.descs, dtype=np.uint64).reshape(-1, C_DESC_WORDS)
+        table[:corpus.nblocks, 1] += np.repeat(delta, corpus.count.astype(np.int64))  # out_offset is the second field
+
+    out = np.zeros(total + 64, dtype=np.uint8)
+    results = (N.BlockResult * max(corpus.nblocks, 1))()
+    if corpus.nblocks:
+        dec = BatchDecoder(device)
+        try:
+            dec.decode(corpus.slab.ctypes.data, corpus.slab.size, corpus.descs, corpus.nblocks, out.ctypes.data, total, N.OUT_PCM, 0, results)
+        finally:
+            dec.close()
+
+    res = []
+    for i, wpc in enumerate(ctxs):
+        if not ok[i]:
+            res.append((b"", 1))
+            continue
+        s = int(pcm_start[i])
+        h, t = heads[i], tails[i]
+        out[s - len(h):s] = np.frombuffer(h, dtype=np.uint8)
+        out[s + pcm_bytes[i]:s + pcm_bytes[i] + len(t)] = np.frombuffer(t, dtype=np.uint8)
+        f, c = int(corpus.first[i]), int(corpus.count[i])
+        crc_errors = sum(1 for k in range(f, f + c) if results[k].rflags & N.RF_CRC_ERROR)
+        total_native = W.WavpackGetNumSamples(wpc, True)
+        loop_samples = int(int(total_native / 100) / SAMPLE_BUFFER_SIZE) * SAMPLE_BUFFER_SIZE  # WvDemo.cs:113, C# division truncates (-1: unknown length)
+        unpacked = int(wpc.info.indexed_samples)
+        if reference_quirks and loop_samples == 0:
+            block_align = W.WavpackGetReducedChannels(wpc) * W.WavpackGetBytesPerSample(wpc)
+            first_chunk = min(unpacked, SAMPLE_BUFFER_SIZE) * block_align
+            res.append((out[s - len(h):s + first_chunk].tobytes(), 1))
+            continue
+        num_samples = W.WavpackGetNumSamples(wpc)
+        code = 1 if (num_samples != -1 and unpacked != num_samples) or crc_errors > 0 else 0  # WvDemo.cs:157-169
+        res.append((out[s - len(h):s + pcm_bytes[i] + len(t)].tobytes(), code))
+    return res
+
+
+C_DESC_WORDS = 144 // 8
