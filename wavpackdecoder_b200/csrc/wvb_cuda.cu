@@ -357,8 +357,10 @@ static int launch_plan(wvb_batch *b, const std::vector<Launch> &plan, const uint
 // Host-buffer decode of a large table, pipelined: the table is cut into segments of consecutive descriptors; segment k's
 // H2D copy, kernels and D2H copy run on three streams so that copies in both directions overlap the kernels of other
 // segments (PCIe is the end-to-end bound: the PCM leaving the GPU is 2x the compressed bytes entering it).
+// out_device: `out` is device memory (WVB_OUT_DEVICE): the kernels write into it directly and nothing is copied back, the
+// upload still overlaps the decode segment by segment (the verify flow: host .wv bytes in, device PCM + MD5 out)
 static int decode_pipelined(wvb_batch *b, const uint8_t *in, size_t in_bytes, const wvb_block_desc *descs, size_t nblocks, uint8_t *out,
-                            size_t out_bytes, int fmt, wvb_block_result *results, bool *used)
+                            size_t out_bytes, int fmt, wvb_block_result *results, bool out_device, bool *used)
 {
     *used = false;
     const int ofmt = fmt == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : fmt;
@@ -418,7 +420,8 @@ static int decode_pipelined(wvb_batch *b, const uint8_t *in, size_t in_bytes, co
         b->seg_ev.push_back(e);
     }
     if ((rc = ensure(b->d_in, b->d_in_cap, in_bytes + 64)) != WVB_OK) return rc;
-    if ((rc = ensure(b->d_out, b->d_out_cap, out_bytes + 64)) != WVB_OK) return rc;
+    if (!out_device && (rc = ensure(b->d_out, b->d_out_cap, out_bytes + 64)) != WVB_OK) return rc;
+    uint8_t *dout = out_device ? out : b->d_out;
     if ((rc = ensure(b->d_results, b->d_results_cap, nblocks + 1)) != WVB_OK) return rc;
     if ((rc = ensure(b->d_descs, b->d_descs_cap, nblocks + 1)) != WVB_OK) return rc;
     if ((rc = ensure(b->d_order, b->d_order_cap, nblocks + 1)) != WVB_OK) return rc;
@@ -451,11 +454,11 @@ static int decode_pipelined(wvb_batch *b, const uint8_t *in, size_t in_bytes, co
         CUDA_TRY(cudaMemcpyAsync(b->d_in + g.in_lo, in + g.in_lo, g.in_hi - g.in_lo, cudaMemcpyHostToDevice, b->s_in));
         CUDA_TRY(cudaEventRecord(b->seg_ev[2 * k], b->s_in));
         CUDA_TRY(cudaStreamWaitEvent(ks, b->seg_ev[2 * k], 0));
-        if ((rc = launch_plan(b, plans[k], b->d_in, b->d_out, fmt, b->d_results, ks)) != WVB_OK) return rc;
+        if ((rc = launch_plan(b, plans[k], b->d_in, dout, fmt, b->d_results, ks)) != WVB_OK) return rc;
         CUDA_TRY(cudaEventRecord(b->seg_ev[2 * k + 1], ks));
         CUDA_TRY(cudaStreamWaitEvent(b->s_out, b->seg_ev[2 * k + 1], 0));
         CUDA_TRY(cudaStreamWaitEvent(s, b->seg_ev[2 * k + 1], 0));
-        CUDA_TRY(cudaMemcpyAsync(out + g.out_lo, b->d_out + g.out_lo, g.out_hi - g.out_lo, cudaMemcpyDeviceToHost, b->s_out));
+        if (!out_device) CUDA_TRY(cudaMemcpyAsync(out + g.out_lo, dout + g.out_lo, g.out_hi - g.out_lo, cudaMemcpyDeviceToHost, b->s_out));
     }
     CUDA_TRY(cudaEventRecord(b->ev[2], s));
     CUDA_TRY(cudaEventRecord(b->seg_ev[2 * segs.size() + 1], b->s_out));
@@ -516,9 +519,11 @@ int wvb_batch_decode(wvb_batch *b, const uint8_t *in, size_t in_bytes, const wvb
     } else if (b->prepared_in_extent > in_bytes || b->prepared_out_extent > out_bytes)
         return set_error(WVB_E_ARG, "slabs smaller than the prepared table needs");
 
-    if (descs && !(mem_flags & (WVB_IN_DEVICE | WVB_OUT_DEVICE | WVB_RESULTS_DEVICE))) {
+    if (descs && !(mem_flags & (WVB_IN_DEVICE | WVB_RESULTS_DEVICE))) {
         bool used = false;
-        if ((rc = decode_pipelined(b, in, in_bytes, descs, nblocks, (uint8_t *)out, out_bytes, out_format, results, &used)) != WVB_OK) return rc;
+        if ((rc = decode_pipelined(b, in, in_bytes, descs, nblocks, (uint8_t *)out, out_bytes, out_format, results, (mem_flags & WVB_OUT_DEVICE) != 0,
+                                   &used)) != WVB_OK)
+            return rc;
         if (used) return (mem_flags & WVB_NO_SYNC) ? WVB_OK : wvb_batch_wait(b);
     }
 
