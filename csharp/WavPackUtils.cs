@@ -69,6 +69,10 @@ namespace WavPack
             void* output, UIntPtr out_bytes, int out_format, uint mem_flags, BlockResult* results);
         [DllImport(Lib)] internal static extern IntPtr wvb_host_alloc(UIntPtr bytes); // pinned host memory
         [DllImport(Lib)] internal static extern void wvb_host_free(IntPtr p);
+        // integrity (beyond the reference, which ignores ID_MD5_CHECKSUM): MD5 of decoded ranges on the device, stored digest lookup
+        [DllImport(Lib)] internal static extern unsafe int wvb_batch_md5(IntPtr batch, void* device_out, UIntPtr out_bytes, ulong* offsets, ulong* lengths,
+            UIntPtr n, byte* digests);
+        [DllImport(Lib)] internal static extern unsafe int wvb_stored_md5(byte* file, UIntPtr len, byte* md5);
         internal const int WVB_OUT_INT32 = 0, WVB_OUT_PCM = 1;
         internal const uint WVB_RF_CRC_ERROR = 1;
     }
