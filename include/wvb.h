@@ -179,7 +179,9 @@ int wvb_index_many(const uint8_t *slab, const uint64_t *offsets, const uint64_t 
                    uint64_t *first, uint64_t *count, uint64_t *file_out_offset, size_t *nblocks, uint64_t *out_bytes);
 
 /* Turn file-relative descriptors into slab-absolute ones: in_offset += in_base;
- * out_offset = out_base + out_offset(samples) * out_stride * unit_bytes. */
+ * out_offset = out_base + out_offset(samples) * out_stride * unit_bytes.
+ * Alignment of out_base: int32 output needs a multiple of 4; packed PCM accepts any offset (block outputs are
+ * assembled into aligned words with bytewise first/last words), 16-bit stereo decodes fastest at multiples of 4. */
 void wvb_rebase(wvb_block_desc *blocks, size_t n, uint64_t in_base, uint64_t out_base, int out_format, uint32_t file_id);
 
 /* bytes one complete sample occupies in the output for this descriptor */

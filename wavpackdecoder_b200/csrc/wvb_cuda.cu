@@ -120,9 +120,10 @@ pcm_kernel_t pcm_kernel(int variant, uint32_t count = 0, int sm_count = 148)
     case wvb::V_MONO | wvb::V_FIXED: return k_decode_pcm<false, false, false, FixM>;
     case wvb::V_STEREO | wvb::V_FIXED: return k_decode_pcm<true, false, false, FixS>;
     case wvb::V_STEREO | wvb::V_FIXED | wvb::V_F16: {
-        // Two builds of the same kernel: 91 registers (5 CTAs/SM, no spills) and, compiled for 6 resident CTAs/SM, 80 registers
-        // with ~50 B of spills.  The second wins once the launch no longer fits one wave of the first (measured on B200:
-        // 200k blocks 114.5 -> 108.4 ms; 80k blocks 49.2 vs 52.7 ms).  WVB_FIXED_OCC overrides for experiments.
+        // Two builds of the same kernel: 90 registers (5 CTAs/SM, no spills) and, compiled for 6 resident CTAs/SM, 80 registers
+        // with ~40 B of spills.  The second wins once the launch no longer fits one wave of the first (measured on B200 at
+        // 200k blocks: 92.9 vs 86.9 ms; capping further to 72 / 64 registers costs more in spills than occupancy returns:
+        // 120 / 124 ms).  WVB_FIXED_OCC=0|6 overrides for experiments.
         static const int env_occ = getenv("WVB_FIXED_OCC") ? atoi(getenv("WVB_FIXED_OCC")) : -1;
         const int occ = env_occ >= 0 ? env_occ : (count > (uint32_t)sm_count * 5u * CTA_THREADS ? 6 : 0);
         if (occ == 6) return k_decode_pcm<true, false, false, FixS, 6, true>;
