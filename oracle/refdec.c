@@ -1747,6 +1747,7 @@ static i64 unpack_dsd_samples(rd_context *wpc, i32 *buffer, long buffer_len, i64
         if (wps->dsd.mode == 0) {
             i64 total_samples = sample_count * ((flags & MONO_DATA) > 0 ? 1 : 2);
             i64 bsp = bufferStartPos;
+            if (!wps->dsd.data) THROW(wpc); /* no ID_DSD_BLOCK seen yet: NullReferenceException in the reference */
             if (wps->dsd.data->len - wps->dsd.byteptr < total_samples) total_samples = wps->dsd.data->len - wps->dsd.byteptr;
             while (total_samples-- > 0) {
                 if (bsp < 0 || bsp >= buffer_len) THROW(wpc);

@@ -44,6 +44,11 @@ def main():
             data[a:a] = bytes(rng.randrange(256) for _ in range(rng.randrange(1, 200)))
         data = bytes(data)
         chunk = rng.choice([4096, 4096, 1000, 333])
+        # a flipped bit in total_samples makes the reference pad zeros up to that count (billions of samples): not worth the minutes
+        tot = max((int.from_bytes(data[p + 12:p + 16], "little") for p in range(0, max(0, len(data) - 32)) if data[p:p + 4] == b"wvpk"), default=0)
+        if tot != 0xffffffff and tot > 4000000:
+            stats["skipped_huge"] = stats.get("skipped_huge", 0) + 1
+            continue
         try:
             ref, errs, status, info = oracle_decode(data, 0, chunk)
         except RuntimeError:
@@ -77,7 +82,7 @@ def main():
                 it, chunk, out.size, ref.size, nd, sum(1 for r in res if r.rflags & 1), errs, [hex(r.rflags) for r in res if r.rflags][:4]))
             with open("/tmp/fuzz_fail_%d.wv" % it, "wb") as f:
                 f.write(data)
-    print(stats)
+    print(stats, flush=True)
     return 1 if stats["mismatch"] else 0
 
 
