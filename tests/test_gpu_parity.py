@@ -202,3 +202,32 @@ def test_fuzzed_batch_on_device(gpu):
         assert same or inexact
         exact += bool(same)
     assert exact >= 120
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(bits=24), dict(bits=8, channels=1), dict(channels=1)], ids=["s16", "s24", "m8", "m16"])
+def test_packed_pcm_at_unaligned_output_offsets(gpu, kw):
+    """A caller-rebased table may put packed PCM at any byte offset of the output slab.  16-bit stereo then leaves its
+    one-word-per-frame kernel (wvb_plan.h block_is_fast16) for the packed writer, whose first and last words are written
+    bytewise; nothing outside the file's byte range may be touched."""
+    import torch
+    from wavpackdecoder_b200.batch import BatchDecoder, Corpus
+    cfg, src, data = make_file(seconds=0.3, block_samples=1001, **kw)
+    ref, errs, status, info = oracle_decode(data, 0, 4096)
+    want = format_samples(ref, info["bytes_per_sample"])
+    dec = BatchDecoder(0)
+    try:
+        for shift in (0, 1, 2, 3, 5):
+            corpus = Corpus.from_files([bytes(data)], out_format=gpu.OUT_PCM)
+            table = np.frombuffer(corpus.descs, dtype=np.uint64).reshape(-1, 18)
+            table[:corpus.nblocks, 1] += shift  # out_offset
+            total = corpus.out_bytes + shift + 7
+            d_out = torch.full((total + 64,), 0xEE, dtype=torch.uint8, device="cuda")
+            results = (gpu.BlockResult * corpus.nblocks)()
+            dec.decode(corpus.slab.ctypes.data, corpus.slab.size, corpus.descs, corpus.nblocks, d_out.data_ptr(), total, gpu.OUT_PCM,
+                       gpu.OUT_DEVICE, results)
+            got = d_out.cpu().numpy()
+            assert np.array_equal(got[shift:shift + want.size], want), shift
+            assert (got[:shift] == 0xEE).all() and (got[shift + want.size:] == 0xEE).all(), shift
+            assert not any(r.rflags for r in results)
+    finally:
+        dec.close()
