@@ -64,6 +64,8 @@ using GenS = wvb::GenericDecorr<true>;
 using GenM = wvb::GenericDecorr<false>;
 using FixS = wvb::FixedDecorr<true, WVB_FIXED_STEREO_TERMS>;
 using FixM = wvb::FixedDecorr<false, WVB_FIXED_MONO_TERMS>;
+using FixSB = wvb::FixedDecorr<true, WVB_FIXED_STEREO_B_TERMS>;
+using FixSC = wvb::FixedDecorr<true, WVB_FIXED_STEREO_C_TERMS>;
 
 } // namespace
 
@@ -129,6 +131,12 @@ pcm_kernel_t pcm_kernel(int variant, uint32_t count = 0, int sm_count = 148)
         if (occ == 6) return k_decode_pcm<true, false, false, FixS, 6, true>;
         return k_decode_pcm<true, false, false, FixS, 0, true>;
     }
+    case wvb::V_STEREO | wvb::V_FIXED_B: return k_decode_pcm<true, false, false, FixSB>;
+    case wvb::V_STEREO | wvb::V_FIXED_B | wvb::V_F16:
+        if (count > (uint32_t)sm_count * 5u * CTA_THREADS) return k_decode_pcm<true, false, false, FixSB, 6, true>;
+        return k_decode_pcm<true, false, false, FixSB, 0, true>;
+    case wvb::V_STEREO | wvb::V_FIXED_C: return k_decode_pcm<true, false, false, FixSC>;
+    case wvb::V_STEREO | wvb::V_FIXED_C | wvb::V_F16: return k_decode_pcm<true, false, false, FixSC, 0, true>;
     case wvb::V_MONO | wvb::V_GENFIX: return k_decode_pcm<false, false, true, GenM>;
     case wvb::V_STEREO | wvb::V_GENFIX: return k_decode_pcm<true, false, true, GenS>;
     case wvb::V_MONO | wvb::V_GENFIX | wvb::V_HYBRID: return k_decode_pcm<false, true, true, GenM>;
@@ -156,19 +164,21 @@ void make_plan(const wvb_block_desc *descs, size_t n, int fmt, std::vector<uint3
         const wvb_block_desc &d = descs[i];
         int v = wvb::variant_of(d);
         // 16-bit interleaved stereo PCM gets its own launches: one aligned word store per frame, no byte-packing state
-        if ((v & ~wvb::V_FIXED) == wvb::V_STEREO && wvb::block_is_fast16(d, fmt == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : fmt)) v |= wvb::V_F16;
+        if ((v & ~(wvb::V_FIXED | wvb::V_FIXED_B | wvb::V_FIXED_C)) == wvb::V_STEREO && wvb::block_is_fast16(d, fmt == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : fmt)) v |= wvb::V_F16;
         int cls = v == wvb::V_DSD ? wvb::dsd_mode_class(d) : smem_class(d.smem_words);
         uint64_t clsbits = (uint64_t)(cls < 0 ? 1023 : cls) & 1023;
         // variant | class | term signature (16 bits) | inverted length (so long blocks start first)
-        key[i] = ((uint64_t)v << 58) | (clsbits << 48) | ((uint64_t)(d.terms_sig & 0xffff) << 32) | (uint64_t)(0xffffffffu - d.block_samples);
+        // variant (8 bits) | class (10) | term signature (16) | inverted length (30; longer blocks saturate, they only lose their order)
+        const uint64_t inv_len = 0x3fffffffu - (d.block_samples < 0x3fffffffu ? d.block_samples : 0x3fffffffu);
+        key[i] = ((uint64_t)v << 56) | (clsbits << 46) | ((uint64_t)(d.terms_sig & 0xffff) << 30) | inv_len;
     }
     std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key[a] != key[b] ? key[a] < key[b] : a < b; });
     launches.clear();
     size_t i = 0;
     while (i < n) {
-        uint64_t k = key[order[i]] >> 48;
+        uint64_t k = key[order[i]] >> 46;
         size_t j = i;
-        while (j < n && (key[order[j]] >> 48) == k) j++;
+        while (j < n && (key[order[j]] >> 46) == k) j++;
         Launch L;
         L.variant = (int)(k >> 10);
         L.cls = (int)(k & 1023);

@@ -7,7 +7,7 @@
 namespace wvb {
 
 // kernel variants of the PCM path
-enum { V_MONO = 0, V_STEREO = 1, V_GENFIX = 2, V_HYBRID = 4, V_DSD = 8, V_FIXED = 16, V_F16 = 32, V_COUNT = 64 };
+enum { V_MONO = 0, V_STEREO = 1, V_GENFIX = 2, V_HYBRID = 4, V_DSD = 8, V_FIXED = 16, V_F16 = 32, V_FIXED_B = 64, V_FIXED_C = 128, V_COUNT = 256 };
 
 // FNV-1a over the term list in DECODER order, as wvb_index computes wvb_block_desc.terms_sig
 constexpr uint32_t terms_hash(const int *t, int n)
@@ -25,6 +25,14 @@ constexpr int kFixedStereo[] = {WVB_FIXED_STEREO_TERMS};
 constexpr int kFixedMono[] = {WVB_FIXED_MONO_TERMS};
 constexpr uint32_t kFixedStereoSig = terms_hash(kFixedStereo, 5);
 constexpr uint32_t kFixedMonoSig = terms_hash(kFixedMono, 4);
+//   stereo {18,18,2,17,3} (V_FIXED_B) and {18,17} (V_FIXED_C): what FFmpeg's encoder writes at its default and fastest
+//   compression levels (tests/golden/ff_s16_stereo_c1.wv, ..._c0.wv); higher levels search a list per block and stay generic
+#define WVB_FIXED_STEREO_B_TERMS 3, 17, 2, 18, 18
+#define WVB_FIXED_STEREO_C_TERMS 17, 18
+constexpr int kFixedStereoB[] = {WVB_FIXED_STEREO_B_TERMS};
+constexpr int kFixedStereoC[] = {WVB_FIXED_STEREO_C_TERMS};
+constexpr uint32_t kFixedStereoBSig = terms_hash(kFixedStereoB, 5);
+constexpr uint32_t kFixedStereoCSig = terms_hash(kFixedStereoC, 2);
 
 // 16-bit interleaved stereo PCM at a 4-byte aligned slab offset, the bench case: one aligned 32-bit store per frame, no
 // byte packing state to carry (a caller-rebased table with odd offsets goes through the packed writer instead)
@@ -46,6 +54,8 @@ inline int variant_of(const wvb_block_desc &d)
         // plain lossless block: use the in-register kernel when its term list is one we specialise (checked again on the device)
         if (v == V_STEREO && d.sub_len[WVB_SUB_TERMS] == 5 && d.terms_sig == kFixedStereoSig) v |= V_FIXED;
         if (v == V_MONO && d.sub_len[WVB_SUB_TERMS] == 4 && d.terms_sig == kFixedMonoSig) v |= V_FIXED;
+        if (v == V_STEREO && d.sub_len[WVB_SUB_TERMS] == 5 && d.terms_sig == kFixedStereoBSig) v |= V_FIXED_B;
+        if (v == V_STEREO && d.sub_len[WVB_SUB_TERMS] == 2 && d.terms_sig == kFixedStereoCSig) v |= V_FIXED_C;
     }
     return v;
 }
