@@ -15,7 +15,7 @@ run "config5 DSD64 stereo mode 0 (raw)" --files 1000 --seconds 10 --kw kind=3 ds
 run "config5 DSD64 stereo mode 1 (fast)" --files 1000 --seconds 10 --kw kind=3 dsd_mode=1 block_samples=22050
 run "config5 DSD64 stereo mode 3 (high)" --files 1000 --seconds 10 --kw kind=3 dsd_mode=3 block_samples=22050
 run "16-bit stereo, generic kernel (terms 18,18,2,3,-2 with a different order)" --files 10000 --seconds 10 --kw terms=18,2,18,3,-2 deltas=2,2,2,2,2
-run "16-bit stereo, generic kernel, FFmpeg/libwavpack default-mode list 18,18,2,17,3" --files 10000 --seconds 10 --kw terms=18,18,2,17,3 deltas=2,2,2,2,2
-run "16-bit stereo, generic kernel, fast-mode list 18,17" --files 10000 --seconds 10 --kw terms=18,17 deltas=2,2
+run "16-bit stereo, FFmpeg default-level list 18,18,2,17,3 (in-register kernel V_FIXED_B)" --files 10000 --seconds 10 --kw terms=18,18,2,17,3 deltas=2,2,2,2,2
+run "16-bit stereo, FFmpeg fastest-level list 18,17 (in-register kernel V_FIXED_C)" --files 10000 --seconds 10 --kw terms=18,17 deltas=2,2
 run "24-bit stereo 44.1k, stock terms (shift-free, plain kernel)" --files 8000 --seconds 10 --kw bits=24
 run "16-bit mono, stock mono terms (in-register kernel)" --files 16000 --seconds 10 --kw channels=1 terms=18,18,2,3 deltas=2,2,2,2

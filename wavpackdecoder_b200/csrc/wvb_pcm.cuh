@@ -727,22 +727,6 @@ WVB_DEV void store_unit(uint8_t *q, int v, int unit, int add128)
     else q[0] = (uint8_t)(v + add128);
 }
 
-// nbytes (<= 8) of `v` to q with the widest naturally aligned stores: a channel pair inside a wider interleaved frame
-// (multichannel files) is 4, 6 or 8 bytes at an even address, i.e. one or two stores instead of one per byte.
-WVB_DEV void store_bytes(uint8_t *q, uint64_t v, int nbytes)
-{
-    while (nbytes > 0) {
-        const uintptr_t a = (uintptr_t)q;
-        int w;
-        if ((a & 1) || nbytes < 2) { *q = (uint8_t)v; w = 1; }
-        else if ((a & 2) || nbytes < 4) { *(uint16_t *)q = (uint16_t)v; w = 2; }
-        else { *(uint32_t *)q = (uint32_t)v; w = 4; }
-        q += w;
-        v >>= 8 * w;
-        nbytes -= w;
-    }
-}
-
 // Packs a block's contiguous output bytes into aligned 32-bit stores.  One store instruction of a warp touches 32
 // different output streams (32 sectors) whatever its width, so 24-bit stereo written byte by byte costs six such
 // instructions per frame and saturates the load/store path (ncu: L1TEX 71 % busy, decoder issue rate 27 %); packed, it is 1.5.
@@ -1045,9 +1029,8 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
                             ow.push((uint32_t)(va + add128) & unit_mask, 8 * unit);
                             if (out_ch == 2) ow.push((uint32_t)((STEREO ? vb : va) + add128) & unit_mask, 8 * unit);
                         } else { // a channel pair (or one channel) inside a wider frame
-                            uint64_t fv = (uint32_t)(va + add128) & unit_mask;
-                            if (out_ch == 2) fv |= (uint64_t)((uint32_t)((STEREO ? vb : va) + add128) & unit_mask) << (8 * unit); // FALSE_STEREO duplicates (UnpackUtils.cs:668-680)
-                            store_bytes(op, fv, unit * out_ch);
+                            store_unit(op, va, unit, add128);
+                            if (out_ch == 2) store_unit(op + unit, STEREO ? vb : va, unit, add128); // FALSE_STEREO duplicates (UnpackUtils.cs:668-680)
                         }
                     }
                     op += frame_bytes;
