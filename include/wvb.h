@@ -170,6 +170,9 @@ int wvb_device_count(void);       /* 0 without a driver/device */
 int wvb_index(const uint8_t *file, size_t len, uint32_t open_flags, uint32_t chunk_samples, wvb_file_info *info,
               wvb_block_desc *blocks, size_t cap, size_t *nblocks);
 
+/* Sizes are the stream's word: like the reference, the index pads a gap in block_index (or a total_samples the blocks never
+ * reach) with zeros, so a damaged or hostile header can ask for billions of output samples.  Callers that decode untrusted
+ * files should bound wvb_file_info.indexed_samples / the out_bytes of wvb_index_many before allocating. */
 /* Index many files with `threads` host threads (<=0: all cores).  File i occupies
  * slab[offsets[i] .. offsets[i]+sizes[i]); its descriptors are written to
  * blocks[first[i] .. first[i]+count[i]) (first/count are outputs) already rebased
