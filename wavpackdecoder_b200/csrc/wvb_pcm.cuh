@@ -166,6 +166,7 @@ struct BitReader {
     }
     WVB_DEV void consume(int n) { pos += n; }
     WVB_DEV uint32_t peek() const { return (uint32_t)((((uint64_t)w1 << 32) | w0) >> pos); } // the next min(32, 64 - pos) bits
+    WVB_DEV uint64_t peek64() const { return (((uint64_t)w1 << 32) | w0) >> pos; }            // the next 64 - pos bits
     WVB_DEV uint32_t getbit() { refill(); const uint32_t b = peek() & 1u; consume(1); return b; }
     WVB_DEV uint32_t getbits(int n) // 0 <= n <= 32
     {
@@ -337,17 +338,25 @@ template <bool HYB, bool STEREO, int CH> WVB_DEV bool decode_word(BitReader &br,
             } else {
                 if (lossless_code)
                     mid = read_code_wide(br, low, range);
-                else { // WordsUtils.cs:477-492
+                else { // WordsUtils.cs:477-492: bisect the interval down to the error limit, one bit per halving
                     uint32_t lim = 0;
                     if constexpr (HYB) lim = (uint32_t)w.errlim[CH];
+                    // at most 32 halvings and the sign bit: all 33 come out of one look at the window (>= 33 valid bits after a
+                    // refill) instead of a refill check, a peek and a position update per bit
+                    br.refill();
+                    const uint64_t win = br.peek64();
+                    int nb = 0;
                     mid = (uint32_t)(((uint64_t)high + low + 1) >> 1);
                     while (high - low > lim) {
-                        if (br.getbit()) low = mid;
+                        if ((win >> nb) & 1u) low = mid;
                         else high = mid - 1;
+                        ++nb;
                         mid = (uint32_t)(((uint64_t)high + low + 1) >> 1);
                     }
+                    sign = (uint32_t)(win >> nb) & 1u;
+                    br.consume(nb + 1);
                 }
-                sign = br.getbit();
+                if (lossless_code) sign = br.getbit();
             }
             out = sign ? (int)~mid : (int)mid; // WordsUtils.cs:494-497
             if constexpr (HYB) {
