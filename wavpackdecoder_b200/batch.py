@@ -172,7 +172,10 @@ def verify_files(files, device=0):
     """Decode a list of .wv byte strings on the GPU and check each file against its stored MD5 without bringing the PCM
     back: the output slab stays in device memory, only 16 bytes per file and the per-block results return.
     Returns a list of dicts: md5 (hex of the decoded PCM), stored (hex or None), match (True/False/None when the file
-    stores no MD5), crc_errors, error (open error message or None)."""
+    stores no MD5), crc_errors, error (open error message or None).
+    The stored digest covers the source file's audio bytes, so `match` is meaningful for lossless integer PCM; float
+    sources (decoded to 24-bit integers here, as by the reference), hybrid-lossy and DSD files (stored digest over the DSD
+    bytes; compare with an OUT_DSD_RAW decode instead) legitimately differ."""
     import torch
     corpus = Corpus.from_files(files, open_flags=0, chunk_samples=4096, out_format=N.OUT_PCM)
     dev = torch.device("cuda", device)
