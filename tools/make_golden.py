@@ -56,6 +56,9 @@ CASES = [
     ("ff_s16_optmono", "s16p", 16, 2, 44100, 0.6, 1, {"optimize_mono": "on"}),
     ("ff_flt_stereo_c1", "fltp", 32, 2, 44100, 0.6, 1, {}),
     ("ff_s16_51_c1", "s16p", 16, 6, 48000, 0.6, 1, {}),
+    ("ff_s16_stereo_c1_long", "s16p", 16, 2, 44100, 3.2, 1, {}),  # seven blocks, incl. the generator's silence gap and L==R stretch
+    ("ff_s24_mono_c1", "s32p", 24, 1, 48000, 0.9, 1, {}),
+    ("ff_u8_mono_c0", "u8p", 8, 1, 22050, 1.1, 0, {}),
 ]
 
 
