@@ -84,3 +84,30 @@ def test_complete_short_files_when_quirks_are_off():
     (out, code), = wvdemo.unpack_files([bytes(data)], reference_quirks=False)
     n = 44100
     assert code == 0 and len(out) == 44 + n * 4 and out[:44] == wvdemo.wave_header(n, 2, 44100, 16, 2)
+
+
+def test_container_host_logic_with_the_device_code_compiled_for_the_host(monkeypatch):
+    """The host side of the container writer (layout, table rebase, header/trailer bytes, exit codes, demo quirks) on a
+    box without a GPU: the batch decoder is replaced by tests/emul (the device decode function compiled for the host, a
+    test harness) and the result compared with the oracle's WvDemo.  The GPU test above runs the real thing."""
+    import ctypes as C
+    from _harness import emul
+    from wavpackdecoder_b200 import wvdemo
+
+    class EmulDecoder:
+        def __init__(self, device=0):
+            self.lib = emul()
+
+        def decode(self, in_ptr, in_bytes, descs, nblocks, out_ptr, out_bytes, out_format, mem_flags=0, results=None):
+            self.lib.emul_decode(C.c_void_p(in_ptr), descs, C.c_size_t(nblocks), C.c_void_p(out_ptr), C.c_int(out_format), results)
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(wvdemo, "BatchDecoder", EmulDecoder)
+    files = _files()
+    got = wvdemo.unpack_files([f for _n, f in files])
+    for (name, f), (data, code) in zip(files, got):
+        ref, ref_code = oracle_wvdemo(f)
+        assert code == ref_code, name
+        assert data == ref, name
