@@ -201,7 +201,10 @@ void wvb_batch_destroy(wvb_batch *b);
  * device slabs (WVB_IN_DEVICE) must be allocated with that slack.  `in` holds the compressed slab (descs' in_offset index it), `out`
  * receives int32 or packed PCM at descs' out_offset.  Host pointers are copied through the
  * batch's device buffers (pinned host memory makes the copies asynchronous); device pointers
- * (WVB_*_DEVICE) are used in place.  descs is always a host pointer.  results may be NULL. */
+ * (WVB_*_DEVICE) are used in place.  descs is always a host pointer.  results may be NULL.
+ * Large host-input batches (>= ~3 GB of input + output, table in slab order) are decoded in segments so that the
+ * upload, the kernels and -- for host output -- the download overlap; with WVB_OUT_DEVICE the PCM stays on the device
+ * (the verify flow, see wvb_batch_md5). */
 int wvb_batch_decode(wvb_batch *b, const uint8_t *in, size_t in_bytes, const wvb_block_desc *descs, size_t nblocks, void *out,
                      size_t out_bytes, int out_format, uint32_t mem_flags, wvb_block_result *results);
 int wvb_batch_wait(wvb_batch *b);
