@@ -438,33 +438,43 @@ static int decode_pipelined(wvb_batch *b, const uint8_t *in, size_t in_bytes, co
     if ((rc = ensure(b->d_order, b->d_order_cap, nblocks + 1)) != WVB_OK) return rc;
     cudaStream_t s = b->stream;
 
-    // per-segment plans over one shared order array
+    // Order of the host work matters here.  The table goes up first; then every segment is planned (a sort), its slice of
+    // the launch order and its slab bytes are queued on the upload stream, and its kernels are launched -- so the first
+    // launch waits for the planning of the (small) first segment only, and the planning of segment k+1 overlaps the upload
+    // and decode of segment k.  (Small copies must not be queued behind the whole slab: the copy engine is first in, first out.)
     b->order.resize(nblocks);
-    std::vector<std::vector<Launch>> plans(segs.size());
-    {
-        std::vector<uint32_t> tmp;
-        for (size_t k = 0; k < segs.size(); k++) {
-            make_plan(descs + segs[k].first, segs[k].count, fmt, tmp, plans[k]);
-            for (size_t j = 0; j < tmp.size(); j++) b->order[segs[k].first + j] = (uint32_t)(tmp[j] + segs[k].first);
-            for (Launch &L : plans[k]) L.first += (uint32_t)segs[k].first;
-        }
-    }
     b->plan.clear();
     b->prepared = false;
-    for (const auto &pl : plans)
-        if ((rc = ensure_dsd_scratch(b, pl)) != WVB_OK) return rc;
     CUDA_TRY(cudaEventRecord(b->ev[0], s));
     CUDA_TRY(cudaMemcpyAsync(b->d_descs, descs, nblocks * sizeof(wvb_block_desc), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(b->d_order, b->order.data(), nblocks * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaEventRecord(b->seg_ev[2 * segs.size()], s));
     CUDA_TRY(cudaStreamWaitEvent(b->s_in, b->seg_ev[2 * segs.size()], 0));
     CUDA_TRY(cudaEventRecord(b->ev[1], s));
+
+    std::vector<std::vector<Launch>> plans(segs.size());
+    std::vector<uint32_t> tmp;
+    auto plan_segment = [&](size_t k) {
+        make_plan(descs + segs[k].first, segs[k].count, fmt, tmp, plans[k]);
+        for (size_t j = 0; j < tmp.size(); j++) b->order[segs[k].first + j] = (uint32_t)(tmp[j] + segs[k].first);
+        for (Launch &L : plans[k]) L.first += (uint32_t)segs[k].first;
+    };
+    // DSD fast mode keeps per-block tables in a scratch buffer that must be sized before the first launch (growing it later
+    // would free memory a running kernel uses): such batches are planned up front
+    bool needs_scratch = false;
+    for (size_t i = 0; i < nblocks && !needs_scratch; i++) needs_scratch = (descs[i].flags & 0x80000000u) != 0;
+    if (needs_scratch) {
+        for (size_t k = 0; k < segs.size(); k++) plan_segment(k);
+        for (const auto &pl : plans)
+            if ((rc = ensure_dsd_scratch(b, pl)) != WVB_OK) return rc;
+    }
     for (size_t k = 0; k < segs.size(); k++) {
         const Seg &g = segs[k];
         cudaStream_t ks = b->seg_streams[k];
+        if (!needs_scratch) plan_segment(k);
+        CUDA_TRY(cudaMemcpyAsync(b->d_order + g.first, b->order.data() + g.first, g.count * sizeof(uint32_t), cudaMemcpyHostToDevice, b->s_in));
         CUDA_TRY(cudaMemcpyAsync(b->d_in + g.in_lo, in + g.in_lo, g.in_hi - g.in_lo, cudaMemcpyHostToDevice, b->s_in));
         CUDA_TRY(cudaEventRecord(b->seg_ev[2 * k], b->s_in));
-        CUDA_TRY(cudaStreamWaitEvent(ks, b->seg_ev[2 * k], 0));
+        CUDA_TRY(cudaStreamWaitEvent(ks, b->seg_ev[2 * k], 0)); // table (s_in waited for it), this segment's order slice and input
         if ((rc = launch_plan(b, plans[k], b->d_in, dout, fmt, b->d_results, ks)) != WVB_OK) return rc;
         CUDA_TRY(cudaEventRecord(b->seg_ev[2 * k + 1], ks));
         CUDA_TRY(cudaStreamWaitEvent(b->s_out, b->seg_ev[2 * k + 1], 0));
