@@ -111,3 +111,32 @@ def test_container_host_logic_with_the_device_code_compiled_for_the_host(monkeyp
         ref, ref_code = oracle_wvdemo(f)
         assert code == ref_code, name
         assert data == ref, name
+
+
+def test_command_line_writes_the_containers(monkeypatch, tmp_path, capsys):
+    import ctypes as C
+    from _harness import emul
+    from wavpackdecoder_b200 import wvdemo
+
+    class EmulDecoder:  # tests/emul stands in for the GPU, as above
+        def __init__(self, device=0):
+            self.lib = emul()
+
+        def decode(self, in_ptr, in_bytes, descs, nblocks, out_ptr, out_bytes, out_format, mem_flags=0, results=None):
+            self.lib.emul_decode(C.c_void_p(in_ptr), descs, C.c_size_t(nblocks), C.c_void_p(out_ptr), C.c_int(out_format), results)
+
+        def close(self):
+            pass
+
+    monkeypatch.setattr(wvdemo, "BatchDecoder", EmulDecoder)
+    a = bytes(make_file(extras=X_RIFF | X_CONFIG | X_MD5_TRAILER, seconds=LONG)[2])
+    b = bytes(make_file(extras=0, bits=24, channels=1, seconds=LONG)[2])
+    (tmp_path / "a.wv").write_bytes(a)
+    (tmp_path / "b.wv").write_bytes(b)
+    code = wvdemo.main([str(tmp_path / "a.wv"), str(tmp_path / "b.wv")])
+    assert code == 0
+    assert (tmp_path / "a.wav").read_bytes() == oracle_wvdemo(a)[0]
+    assert (tmp_path / "b.wav").read_bytes() == oracle_wvdemo(b)[0]
+    out = capsys.readouterr().out
+    assert "2 channels, 16 bits per sample, 44100 samples/s" in out and "1 channels, 24 bits per sample" in out
+    assert wvdemo.main([str(tmp_path / "missing.wv")]) == 1

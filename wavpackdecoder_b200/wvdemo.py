@@ -118,3 +118,50 @@ def unpack_files(files, device=0, reference_quirks=True):
 
 
 C_DESC_WORDS = 144 // 8
+
+
+def main(argv=None):
+    """`python -m wavpackdecoder_b200.wvdemo a.wv [b.wv ...]`: WvDemo's command line over a batch (WvDemo.cs:15-174).
+    Every input is decoded in one device pass and written next to it with the extension the file recommends
+    (WavpackGetFileExtension, "wav" unless the file says otherwise).  Prints the summary lines of WvDemo.cs:57-69 per
+    file; the exit code is 1 if any file's would be (the demo's per-file codes, including its short-file quirk)."""
+    import os
+    import sys
+    args = list(sys.argv[1:] if argv is None else argv)
+    if not args:
+        args = ["input.wv"]  # WvDemo.cs:22
+    blobs, names = [], []
+    for path in args:
+        try:
+            with open(path, "rb") as f:
+                blobs.append(f.read())
+            names.append(path)
+        except OSError:
+            print("Input file '%s' not found" % path, file=sys.stderr)  # WvDemo.cs:30-39
+            return 1
+    results = unpack_files(blobs)
+    corpus = Corpus.from_files(blobs, open_flags=0, chunk_samples=SAMPLE_BUFFER_SIZE, out_format=N.OUT_PCM)  # getters only
+    worst = 0
+    for i, (path, (data, code)) in enumerate(zip(names, results)):
+        wpc = _context(corpus, i)
+        err = W.WavpackGetErrorMessage(wpc)
+        if err:
+            print("Error: " + err, file=sys.stderr)  # WvDemo.cs:41-46
+            worst = 1
+            continue
+        version = W.WavpackGetVersion(wpc)
+        print("The WavPack %s (%d.%d) file '%s' has:" % ("5" if W.WavpackGetIsFive(wpc) else "4", version >> 8, version & 0xff, os.path.basename(path)))
+        print("%d channels, %d bits per sample, %d samples/s, %d total samples, %s decoding" % (
+            W.WavpackGetReducedChannels(wpc), W.WavpackGetBitsPerSample(wpc), W.WavpackGetSampleRate(wpc),
+            W.WavpackGetNumSamples(wpc, True), "Lossy" if W.WavpackLossy(wpc) else "Lossless"))
+        out_path = os.path.splitext(path)[0] + "." + W.WavpackGetFileExtension(wpc)
+        with open(out_path, "wb") as f:
+            f.write(data)
+        if code:
+            print("%s: exit code %d (sample count mismatch, CRC errors, or the demo's short-file exception)" % (path, code), file=sys.stderr)
+        worst = max(worst, code)
+    return worst
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())
