@@ -115,6 +115,27 @@ def _blocks(data):
     return out
 
 
+# damaged streams whose decode depends on state an EARLIER block left in the reference's decoder (quirk C-8): the device
+# decodes every block from its own bytes, so these must come back FLAGGED (WVB_RF_INEXACT) and never fault; samples may differ
+INEXACT_BY_DESIGN = {"dsd1_truncated", "dsd3_truncated", "block2_terms_to_dummy",
+                     "block2_entropy_to_dummy", "mono_block1_terms_to_dummy", "block2_terms_dummy_first_block_too"}
+
+
+def _subblocks(data, off):
+    """(id byte offset, id, payload offset, padded payload length) of every sub-block of the block at `off`."""
+    import struct
+    cks = struct.unpack_from("<I", data, off + 4)[0]
+    at, end, out = off + 32, off + 8 + cks, []
+    while at + 2 <= end:
+        idb, words, hdr = data[at], data[at + 1], 2
+        if idb & 0x80:
+            words |= (data[at + 2] << 8) | (data[at + 3] << 16)
+            hdr = 4
+        out.append((at, idb & 0x3f, at + hdr, words * 2))
+        at += hdr + words * 2
+    return out
+
+
 def corrupt_cases():
     """(name, bytes, open_flags, chunk): damaged streams, the domain's "erasures".  Expected behaviour is whatever the
     oracle does: mute from the start of the caller chunk, CRC error counts, truncated output, gap zero fill, 0x55 DSD mute."""
@@ -163,4 +184,19 @@ def corrupt_cases():
     bad[bl[1][0] + 32] = 0x01
     out.append(("bad_metadata_id_midstream", bytes(bad), 0, 4096))
     out.append(("truncated_in_metadata", data[:bl[2][0] + 40], 0, 4096))
+    # sub-block surgery: a block that loses one of its sub-blocks decodes with the state the previous block left behind.
+    # weights without terms used to index shared memory at -1 on the device: the terms id becomes ID_DUMMY
+    for name, sub_id in (("terms", 2), ("weights", 3), ("samples", 4), ("entropy", 5)):
+        d = bytearray(data)
+        at = [s for s in _subblocks(data, bl[2][0]) if s[1] == sub_id][0][0]
+        d[at] &= ~0x3f
+        out.append(("block2_%s_to_dummy" % name, bytes(d), 0, 4096))
+    dm = bytearray(datam)
+    dm[[s for s in _subblocks(datam, blm[1][0]) if s[1] == 2][0][0]] &= ~0x3f
+    out.append(("mono_block1_terms_to_dummy", bytes(dm), 0, 4096))
+    # a shorter term list with the longer weights sub-block of the original (count checked against the carried terms only when longer)
+    d = bytearray(data)
+    t_at, _, t_pay, t_len = [s for s in _subblocks(data, bl[2][0]) if s[1] == 2][0]
+    d[t_at] = 0x00  # the 5-term list becomes a dummy ...
+    out.append(("block2_terms_dummy_first_block_too", bytes(d[:bl[1][0]]) + bytes(d[bl[2][0]:]), 0, 4096))
     return out

@@ -12,7 +12,9 @@
 namespace {
 struct HostSM {
     std::vector<int> w;
-    int &operator()(int i) { return w[(size_t)i]; }
+    int cap_words = 0;
+    int &operator()(int i) { return w.at((size_t)i); } // bounds-checked: an out-of-range slot index is a device fault
+    int cap() const { return cap_words; }
 };
 }
 
@@ -21,7 +23,8 @@ extern "C" int emul_decode(const uint8_t *in, const wvb_block_desc *descs, size_
     for (size_t i = 0; i < n; i++) {
         const wvb_block_desc &D = descs[i];
         HostSM sm;
-        sm.w.assign((size_t)D.smem_words + 64, 0);
+        sm.w.assign((size_t)D.smem_words + 1, 0);
+        sm.cap_words = (int)D.smem_words;
         wvb_block_result r;
         memset(&r, 0, sizeof(r));
         switch (wvb::variant_of(D)) {

@@ -45,6 +45,12 @@ struct Launch { int variant; int cls; uint32_t first, count; };
 struct SharedColumn { // word i of this thread's column; [slot][thread] layout
     int *base;
     __device__ __forceinline__ int &operator()(int i) { return base[i * CTA_THREADS]; }
+    __device__ __forceinline__ int cap() const // words per thread this launch's dynamic shared memory provides
+    {
+        uint32_t bytes;
+        asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(bytes));
+        return (int)(bytes / (CTA_THREADS * sizeof(int)));
+    }
 };
 
 template <bool STEREO, bool HYB, bool GENFIX, class DEC, int MINB = 0, bool F16 = false>
@@ -296,14 +302,28 @@ int wvb_batch_md5(wvb_batch *b, const void *device_out, size_t out_bytes, const 
 
 static int validate_table(const wvb_block_desc *descs, size_t nblocks, size_t in_bytes, size_t out_bytes, int out_format)
 {
-    for (size_t i = 0; i < nblocks; i++) { // every descriptor must stay inside the slabs (protects the device from bad tables)
+    // Every descriptor must stay inside the slabs and inside its own frame: the table is the caller's word (wvb_index makes
+    // well-formed ones, but a table can be hand-made or rebased wrongly) and the kernels trust it.  Comparisons are written
+    // so that nothing wraps in 64 bits.
+    const int ofmt = out_format == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : out_format;
+    for (size_t i = 0; i < nblocks; i++) {
         const wvb_block_desc &d = descs[i];
-        if (d.in_offset + d.in_bytes > in_bytes) return set_error(WVB_E_ARG, "descriptor input range outside the slab");
-        uint64_t fb = wvb_frame_bytes(&d, out_format == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : out_format);
-        uint64_t lo = d.out_offset - (uint64_t)d.gap_before * fb, hi = d.out_offset + (uint64_t)d.block_samples * fb;
-        if (lo > d.out_offset || hi > out_bytes) return set_error(WVB_E_ARG, "descriptor output range outside the slab");
+        if (d.in_bytes > in_bytes || d.in_offset > in_bytes - d.in_bytes) return set_error(WVB_E_ARG, "descriptor input range outside the slab");
+        if ((unsigned)d.out_ch_offset + d.out_channels > d.out_stride || d.out_channels == 0)
+            return set_error(WVB_E_ARG, "descriptor channel slots outside its output frame");
+        if (ofmt == WVB_OUT_PCM && (d.out_bps < 1 || d.out_bps > 4)) return set_error(WVB_E_ARG, "descriptor bytes per sample not in 1..4");
+        const uint64_t fb = wvb_frame_bytes(&d, ofmt);
+        // bytes written before out_offset: the zero-filled gap, and for DSD the mute fill, which starts at the caller chunk
+        // that contains the end of the block and may therefore reach back into the previous block's output (DsdUtils.cs:99-117)
+        uint64_t back = (uint64_t)d.gap_before * fb;
+        if ((d.flags & 0x80000000u) && d.chunk_first != 0 && d.chunk_first < d.chunk_samples)
+            back = std::max<uint64_t>(back, (uint64_t)(d.chunk_samples - d.chunk_first) * fb);
+        const uint64_t fwd = (uint64_t)d.block_samples * fb; // < 2^32 * 1020
+        if (d.out_offset > out_bytes || fwd > out_bytes - d.out_offset) return set_error(WVB_E_ARG, "descriptor output range outside the slab");
+        if (back > d.out_offset) return set_error(WVB_E_ARG, "descriptor gap / mute fill starts before the slab");
+        if (d.sub_len[WVB_SUB_TERMS] > 16) return set_error(WVB_E_ARG, "more than 16 decorrelation terms");
         for (int k = 0; k < WVB_SUB_COUNT; k++)
-            if (d.sub_off[k] && (uint64_t)d.sub_off[k] + d.sub_len[k] > d.in_bytes) return set_error(WVB_E_ARG, "sub-block outside its block");
+            if (d.sub_off[k] && ((uint64_t)d.sub_off[k] + d.sub_len[k] > d.in_bytes)) return set_error(WVB_E_ARG, "sub-block outside its block");
     }
     return WVB_OK;
 }
@@ -370,8 +390,33 @@ static int launch_plan(wvb_batch *b, const std::vector<Launch> &plan, const uint
 // segments (PCIe is the end-to-end bound: the PCM leaving the GPU is 2x the compressed bytes entering it).
 // out_device: `out` is device memory (WVB_OUT_DEVICE): the kernels write into it directly and nothing is copied back, the
 // upload still overlaps the decode segment by segment (the verify flow: host .wv bytes in, device PCM + MD5 out)
+static int decode_pipelined_queue(wvb_batch *b, const uint8_t *in, size_t in_bytes, const wvb_block_desc *descs, size_t nblocks, uint8_t *out,
+                                  size_t out_bytes, int fmt, wvb_block_result *results, bool out_device, bool *used);
+
 static int decode_pipelined(wvb_batch *b, const uint8_t *in, size_t in_bytes, const wvb_block_desc *descs, size_t nblocks, uint8_t *out,
                             size_t out_bytes, int fmt, wvb_block_result *results, bool out_device, bool *used)
+{
+    const int rc = decode_pipelined_queue(b, in, in_bytes, descs, nblocks, out, out_bytes, fmt, results, out_device, used);
+    if (rc != WVB_OK) {
+        // Work may already be queued (uploads from `in`, kernels on the device slabs, downloads into `out`): the caller is
+        // about to see an error and may free its buffers, so nothing may still be in flight when we return.
+        const std::string msg = g_last_error;
+        if (b->s_in) cudaStreamSynchronize(b->s_in);
+        for (cudaStream_t st : b->seg_streams) cudaStreamSynchronize(st);
+        if (b->s_out) cudaStreamSynchronize(b->s_out);
+        cudaStreamSynchronize(b->stream);
+        cudaGetLastError();
+        b->plan.clear();
+        b->order.clear();
+        b->prepared = false;
+        b->pending_copy = false;
+        g_last_error = msg;
+    }
+    return rc;
+}
+
+static int decode_pipelined_queue(wvb_batch *b, const uint8_t *in, size_t in_bytes, const wvb_block_desc *descs, size_t nblocks, uint8_t *out,
+                                  size_t out_bytes, int fmt, wvb_block_result *results, bool out_device, bool *used)
 {
     *used = false;
     const int ofmt = fmt == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : fmt;
@@ -504,7 +549,7 @@ int wvb_batch_prepare(wvb_batch *b, const wvb_block_desc *descs, size_t nblocks,
     if (nblocks > 0xfffffff0ull) return WVB_E_ARG;
     CUDA_TRY(cudaSetDevice(b->device));
     b->prepared = false;
-    int rc = validate_table(descs, nblocks, ~(size_t)0 >> 1, ~(size_t)0 >> 1, out_format);
+    int rc = validate_table(descs, nblocks, ~(size_t)0 >> 2, ~(size_t)0 >> 2, out_format);
     if (rc != WVB_OK) return rc;
     if ((rc = upload_table(b, descs, nblocks, out_format)) != WVB_OK) return rc;
     CUDA_TRY(cudaStreamSynchronize(b->stream));

@@ -538,6 +538,12 @@ void index_reference_order(Ctx &c, uint32_t chunk, Sink &out)
         B.out_stride = (uint8_t)out_ch;
         B.out_ch_offset = 0;
         B.out_bps = (uint8_t)I.bytes_per_sample;
+        if (B.out_channels > B.out_stride) {
+            // a stereo block in a file whose config says one channel: the reference writes two entries per sample into a
+            // buffer it advances by one, each piece overwriting half of the previous one.  Not reproduced: zeros, flagged.
+            B.out_channels = B.out_stride;
+            B.bflags |= WVB_BF_MUTE_ALL | WVB_BF_STALE_STATE;
+        }
         out.push(B);
         int64_t left = n_block;
         while (left > 0) {
@@ -575,6 +581,7 @@ void index_all_channels(Ctx &c, uint32_t chunk, Sink &out)
         B.out_stride = (uint8_t)I.num_channels;
         B.out_ch_offset = (uint8_t)ch_off;
         B.out_bps = (uint8_t)I.bytes_per_sample;
+        if (ch_off + B.out_channels > I.num_channels) continue; // more coded channels than the file's config declares: no slot to put them in
         ch_off += B.out_channels;
         out.push(B);
         I.indexed_samples = std::max<int64_t>(I.indexed_samples, h.block_index + (int64_t)h.block_samples);
@@ -697,13 +704,18 @@ int wvb_index_many(const uint8_t *slab, const uint64_t *offsets, const uint64_t 
         for (auto &t : th) t.join();
     }
     uint64_t total = 0, obytes = 0;
+    std::vector<uint64_t> own_offsets; // the caller may not want the per-file offsets; pass 2 needs them either way
+    if (!file_out_offset) {
+        own_offsets.resize(nfiles);
+        file_out_offset = own_offsets.data();
+    }
     for (size_t i = 0; i < nfiles; i++) {
         first[i] = total;
         total += count[i];
         uint32_t unit = out_format == WVB_OUT_INT32 ? 4u : (uint32_t)infos[i].bytes_per_sample;
         uint32_t ch = (open_flags & WVB_OPEN_ALL_CHANNELS) ? (uint32_t)infos[i].num_channels
                                                            : (uint32_t)(infos[i].reduced_channels > 0 ? infos[i].reduced_channels : infos[i].num_channels);
-        if (file_out_offset) file_out_offset[i] = obytes;
+        file_out_offset[i] = obytes;
         obytes += (uint64_t)infos[i].indexed_samples * unit * ch;
         obytes = (obytes + 15) & ~(uint64_t)15;
     }
@@ -719,9 +731,7 @@ int wvb_index_many(const uint8_t *slab, const uint64_t *offsets, const uint64_t 
             size_t n = 0;
             wvb_file_info tmp;
             wvb_index(slab + offsets[i], (size_t)sizes[i], open_flags, chunk_samples, &tmp, blocks + first[i], (size_t)count[i], &n);
-            uint64_t obase = 0;
-            if (file_out_offset) obase = file_out_offset[i];
-            wvb_rebase(blocks + first[i], n, offsets[i], obase, out_format, (uint32_t)i);
+            wvb_rebase(blocks + first[i], n, offsets[i], file_out_offset[i], out_format, (uint32_t)i);
         }
     };
     {

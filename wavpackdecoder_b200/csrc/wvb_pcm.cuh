@@ -830,7 +830,11 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
     if (D.bflags & WVB_BF_STALE_STATE) rflags |= WVB_RF_INEXACT;
 
     // ---- metadata contents -> state ----
-    const int nterms = (int)D.sub_len[WVB_SUB_TERMS];
+    // The table is the caller's word: a term count or a state size beyond what this launch provides decodes nothing and is
+    // reported (wvb_index never emits such a block; a hand-made or damaged table must not reach shared memory out of bounds)
+    int nterms = (int)D.sub_len[WVB_SUB_TERMS];
+    bool state_ok = nterms <= 16 && (int)D.smem_words <= SM.cap();
+    if (!state_ok) nterms = 0;
     {
         const uint8_t *tp = blk + D.sub_off[WVB_SUB_TERMS];
         int base = nterms;
@@ -842,6 +846,7 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
             const int mask = ring_mask(term);
             SM(d) = (int)pack_pass(term, delta, mask, base);
             const int words = STEREO ? 2 + 2 * (mask + 1) : 1 + (mask + 1);
+            if (base + words > SM.cap()) { state_ok = false; nterms = d; break; } // smem_words understated the need
             for (int k = 0; k < words; ++k) SM(base + k) = 0;
             base += words;
         }
@@ -849,6 +854,9 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
         const uint8_t *wp = blk + D.sub_off[WVB_SUB_WEIGHTS];
         int cnt = (int)D.sub_len[WVB_SUB_WEIGHTS];
         if (STEREO) cnt >>= 1;
+        // the index pass checks the count against the term count it CARRIES (like the reference); this block's own list can
+        // be shorter or absent (weights without terms after a normal block: stale state), so clamp to what was laid out here
+        if (cnt > nterms) cnt = nterms;
         for (int j = 0; j < cnt; ++j) {
             const int d = nterms - 1 - j;
             const int b0 = (int)((uint32_t)SM(d) >> 16);
@@ -908,7 +916,7 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
     }
 
     DEC dec;
-    const bool terms_ok = dec.load(SM, nterms); // fixed-list kernels refuse (loudly) a block whose terms differ
+    const bool terms_ok = dec.load(SM, nterms) && state_ok; // fixed-list kernels refuse (loudly) a block whose terms differ
     if (!terms_ok) n = 0;
     Words<HYB> w;
     {
@@ -1074,8 +1082,8 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
             }
             for (int c = 0; c < out_ch; ++c) store_unit(q + c * unit, z, unit, add128);
         }
-        res->mute_from = piece_start;
-    } else
+        if (valid) res->mute_from = piece_start;
+    } else if (valid && !mute_all) // (tail lanes alias the last block's result slot: they must not store into it)
         res->mute_from = n;
 
     if (!valid || mute_all) return;
