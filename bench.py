@@ -380,7 +380,7 @@ def main():
         e_elapsed_max = max_over_ranks(e_elapsed, dev)
         e2e_ok = all((results[i].rflags == 0) for i in range(0, cp.nblocks, max(1, cp.nblocks // 1000)))
         e2e = {"value": total_samples * world * args.steps / e_elapsed_max, "unit": UNIT,
-               "h2d_bytes_per_step": int(slab.size + cp.nblocks * (144 + 4)), "d2h_bytes_per_step": int(pcm_bytes + cp.nblocks * 16),
+               "h2d_bytes_per_step": int(slab.size + cp.nblocks * (160 + 4)), "d2h_bytes_per_step": int(pcm_bytes + cp.nblocks * 16),
                "includes": "host block-index pass + H2D + kernels + D2H", "validated": bool(e2e_ok)}
 
     # ---- verify-only end to end: host .wv bytes in, PCM stays in HBM, MD5 per file computed on the device,
@@ -412,7 +412,7 @@ def main():
             ln = int(c2.infos[i].indexed_samples) * 4
             v_ok = v_ok and hashlib.md5(out_np[o:o + ln].tobytes()).digest() == digests[i].tobytes()
         e2e_verify = {"value": total_samples * world * args.steps / v_elapsed, "unit": UNIT,
-                      "h2d_bytes_per_step": int(slab.size + cp.nblocks * (144 + 4) + c2.nfiles * 16),
+                      "h2d_bytes_per_step": int(slab.size + cp.nblocks * (160 + 4) + c2.nfiles * 16),
                       "d2h_bytes_per_step": int(c2.nfiles * 16 + cp.nblocks * 16),
                       "includes": "host block-index pass + H2D + kernels + device MD5 per file; PCM never leaves HBM", "validated": bool(v_ok)}
         del d_out

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define WVB_ABI_VERSION 1
+#define WVB_ABI_VERSION 2
 
 /* status codes */
 enum {
@@ -80,7 +80,7 @@ enum {
 
 /*
  * One decodable block, as produced by wvb_index (file-relative offsets) and consumed
- * by wvb_batch_decode (slab-absolute offsets, see wvb_rebase).  144 bytes.
+ * by wvb_batch_decode (slab-absolute offsets, see wvb_rebase).  160 bytes.
  * Replaces: WavpackHeader (WavpackHeader.cs:15-22) + the WavpackMetadata walk of
  * unpack_init (UnpackUtils.cs:24-68, MetadataUtils.cs:15-109).
  */
@@ -109,6 +109,11 @@ typedef struct wvb_block_desc {
     uint32_t file_id;       /* caller tag */
     uint32_t gap_before;    /* samples of zero fill before this block (WavPackUtils.cs:227-251) */
     uint32_t terms_sig;     /* hash of (terms, deltas): the planner groups equal signatures into the same warps */
+    uint32_t skip_samples;  /* wvb_index_seek: leading samples of the block that seek() decodes and discards in pieces of ... */
+    uint32_t skip_chunk;    /* ... this many samples (SAMPLE_BUFFER_SIZE / channels, WavPackUtils.cs:573-578); both 0 otherwise */
+    uint32_t avg_block_size; /* wphdr.average_block_size after this block's header was read (WavPackUtils.cs:647-650): the
+                                reference's seek() extrapolates file positions from it */
+    uint32_t reserved;
 } wvb_block_desc;
 
 /* per-block result.  Replaces wps.crc / mute_error / check_crc_error (UnpackUtils.cs:1414-1421). 16 bytes */
@@ -159,6 +164,10 @@ typedef struct wvb_file_info {
 
 /* ---- library ---- */
 int wvb_abi_version(void);
+/* The struct layouts this build was compiled with, as text: "struct:size;field:offset:size;...|struct:..." for
+ * wvb_block_desc, wvb_block_result, wvb_file_info and wvb_seek_state.  Host-language bindings that mirror the structs by
+ * hand (ctypes, C# StructLayout) compare themselves with it at start-up or in their tests. */
+const char *wvb_abi_layout(void);
 const char *wvb_last_error(void); /* thread-local text for the last non-OK status */
 int wvb_device_count(void);       /* 0 without a driver/device */
 
@@ -169,6 +178,40 @@ int wvb_device_count(void);       /* 0 without a driver/device */
  * blocks may be NULL with cap 0 to count. */
 int wvb_index(const uint8_t *file, size_t len, uint32_t open_flags, uint32_t chunk_samples, wvb_file_info *info,
               wvb_block_desc *blocks, size_t cap, size_t *nblocks);
+
+/* Seek (replaces seek(), WavPackUtils.cs:521-594, reached through SetSample / SetTime :502-512).
+ *
+ * The reference's reader state a seek starts from: the header it read last and where the file pointer stands.  From a
+ * descriptor of the block the caller read last (or the first block, if nothing was read yet): hdr_pos = in_offset,
+ * ck_size = in_bytes - 8, block_index / block_samples / avg_block_size as in the descriptor, file_pos = in_offset + in_bytes. */
+typedef struct wvb_seek_state {
+    int64_t hdr_pos;        /* wphdr.stream_position */
+    int64_t block_index;
+    int64_t avg_block_size; /* wphdr.average_block_size */
+    int64_t file_pos;       /* infile.BaseStream.Position */
+    uint32_t block_samples;
+    uint32_t ck_size;
+} wvb_seek_state;
+
+/* Index the file as the reference decodes it AFTER seek() to complete sample `target` followed by WavpackUnpackSamples
+ * calls of `chunk_samples`.  The reference probes for a block whose header range contains the target (at most 25 header
+ * reads steered by the average block size), restarts its decoder there with a fresh stream state, and decodes and
+ * discards that block's samples before the target in pieces of `skip_chunk` samples (SAMPLE_BUFFER_SIZE / reduced
+ * channels; 0 selects that); the caller's call grid starts at the target.
+ *   from != NULL: the probe sequence is replayed on the headers exactly (including its quirks: a target that is the first
+ *                 sample of a block is usually reached by decoding the whole previous block, whose CRC verdict then counts;
+ *                 when the probes run out the last header read is taken, wherever it is);
+ *   from == NULL: the block is found by a header hop from the start of the file (what a new caller wants).
+ * Descriptors come back for the block decoding restarts at and up to max_blocks - 1 following ones (0: to the end of the
+ * file), out_offset counted from that block's first sample (*window_first_sample in the file).  *landed_sample is the
+ * sample index the reader stands at afterwards (the target, except after a failed probe sequence): the caller's data begins
+ * *landed_sample - *window_first_sample samples into the decoded window.
+ * info describes the FILE (as wvb_index), except num_blocks / indexed_samples / stopped_early, which describe the window.
+ * Returns WVB_OK with *nblocks == 0 where the reference's seek() returns false (target past the end, unknown length, a
+ * probe before the start of the file) or -- from == NULL -- when no block contains the target. */
+int wvb_index_seek(const uint8_t *file, size_t len, uint32_t open_flags, const wvb_seek_state *from, int64_t target, uint32_t skip_chunk,
+                   uint32_t chunk_samples, size_t max_blocks, wvb_file_info *info, wvb_block_desc *blocks, size_t cap, size_t *nblocks,
+                   int64_t *window_first_sample, int64_t *landed_sample);
 
 /* Sizes are the stream's word: like the reference, the index pads a gap in block_index (or a total_samples the blocks never
  * reach) with zeros, so a damaged or hostile header can ask for billions of output samples.  Callers that decode untrusted

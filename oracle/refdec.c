@@ -1857,26 +1857,21 @@ static void ctx_init(rd_context *wpc, const uint8_t *file, size_t len)
     wpc->stream.wvxbits.is_null = 1;
 }
 
-rd_context *rd_open(const uint8_t *file, size_t len, uint32_t flags) /* WavPackUtils.cs:36-120 */
+/* WavpackOpenFileInput (WavPackUtils.cs:36-120) after `new WavpackContext()`: reads from the stream's current position */
+static void open_input(rd_context *wpc, uint32_t flags)
 {
-    rd_context *wpc = (rd_context *)malloc(sizeof(rd_context));
-    ctx_init(wpc, file, len);
     WavpackStream *wps = &wpc->stream;
 
     wpc->total_samples = -1;
-    if (setjmp(wpc->jb)) {
-        wpc->error_message = "exception";
-        return wpc;
-    }
     while (wps->wphdr.block_samples == 0) {
         read_next_header(wpc);
         if (wps->wphdr.error) {
             wpc->error_message = "not compatible with this version of WavPack file!";
-            return wpc;
+            return;
         }
         if (wps->wphdr.block_samples > 0 && wps->wphdr.total_samples != 0xFFFFFFFFLL)
             wpc->total_samples = wps->wphdr.total_samples;
-        if (!unpack_init(wpc)) return wpc;
+        if (!unpack_init(wpc)) return;
     }
 
     wpc->config.flags = wpc->config.flags & ~0xffLL;
@@ -1902,29 +1897,49 @@ rd_context *rd_open(const uint8_t *file, size_t len, uint32_t flags) /* WavPackU
         wpc->reduced_channels = (wps->wphdr.flags & MONO_FLAG) != 0 ? 1 : 2;
     if ((flags & RD_OPEN_2CH_MAX) == 0 && wpc->config.num_channels > 2) {
         wpc->error_message = "only two channels supported!";
-        return wpc;
+        return;
     }
     if ((wps->wphdr.flags & DSD_FLAG) != 0) {
         wpc->config.bytes_per_sample = 1;
         wpc->config.bits_per_sample = 8;
     }
+}
+
+rd_context *rd_open(const uint8_t *file, size_t len, uint32_t flags) /* WavPackUtils.cs:36-120 */
+{
+    rd_context *wpc = (rd_context *)malloc(sizeof(rd_context));
+    ctx_init(wpc, file, len);
+    if (setjmp(wpc->jb)) {
+        wpc->error_message = "exception";
+        return wpc;
+    }
+    open_input(wpc, flags);
     return wpc;
 }
 
-void rd_close(rd_context *c)
+static void stream_release(WavpackStream *s) /* what the garbage collector does to a dropped WavpackStream */
 {
-    if (!c) return;
-    WavpackStream *s = &c->stream;
     if (!s->wvbits.is_null) ba_unref(s->wvbits.buf);
     if (!s->wvcbits.is_null) ba_unref(s->wvcbits.buf);
     if (!s->wvxbits.is_null) ba_unref(s->wvxbits.buf);
     dsd_free(&s->dsd);
+}
+
+static void ctx_release_rest(rd_context *c) /* everything of a context except its stream */
+{
     md_set_data(&c->md, NULL);
     free(c->read_buffer.p);
     free(c->file_extension);
     free(c->header);
     free(c->trailer);
     free(c);
+}
+
+void rd_close(rd_context *c)
+{
+    if (!c) return;
+    stream_release(&c->stream);
+    ctx_release_rest(c);
 }
 
 long rd_unpack_samples(rd_context *wpc, int32_t *buffer, long buffer_len, long samples_in) /* WavPackUtils.cs:200-282 */
@@ -1989,6 +2004,95 @@ long rd_unpack_samples(rd_context *wpc, int32_t *buffer, long buffer_len, long s
         if (wps->sample_index == wpc->total_samples) break;
     }
     return (long)samples_unpacked;
+}
+
+/* seek (WavPackUtils.cs:521-594), reached through SetSample / SetTime (WavPackUtils.cs:502-512).
+ * Returns 1 / 0 like the C# bool; -2 where the C# code would throw out of the call (anything but the IOException it
+ * catches: divide by zero on a zero-length block, an IndexOutOfRange inside the nested open or unpack); -3 where it would
+ * never return (`index -= toUnpack` with WavpackUnpackSamples stuck at 0, WavPackUtils.cs:573-578). */
+static int seek_impl(rd_context *wpc, i64 targetSample)
+{
+    WavpackStream *wps = &wpc->stream;
+    MemStream *infile = &wpc->infile;
+
+    if (targetSample >= wpc->total_samples) return 0;
+    if (targetSample < 0) targetSample = 0;
+
+    int steps = 25;      /* maximum steps to position */
+    const int min = 5;   /* min count of block for seek forward by just read header */
+
+    while (steps-- > 0) {
+        i64 seek_pos = wps->wphdr.stream_position;
+
+        if (targetSample <= (i64)wps->wphdr.block_samples)
+            seek_pos = 0;
+        else if (targetSample < wps->wphdr.block_index || targetSample > wps->wphdr.block_index + (i64)wps->wphdr.block_samples) {
+            i64 distance = targetSample - wps->wphdr.block_index;
+            /* int * uint promotes to long in C# */
+            distance += distance > 0 ? (-1 * (i64)wps->wphdr.block_samples + 1) : (-2 * (i64)wps->wphdr.block_samples + 1);
+            if (wps->wphdr.block_samples == 0) return -2; /* DivideByZeroException is not an IOException */
+            i64 blocks = distance / (i64)wps->wphdr.block_samples;
+            if (blocks >= 0 && blocks <= min)
+                seek_pos = -1;
+            else
+                seek_pos += blocks * wps->wphdr.average_block_size;
+            if (seek_pos >= infile->len) seek_pos = -1;
+        }
+
+        if (seek_pos != -1) {
+            if (seek_pos < 0) return 0; /* Stream.Seek before the beginning throws IOException: caught, `return false` */
+            infile->pos = seek_pos;
+        }
+
+        read_next_header(wpc);
+        if (wps->wphdr.error) continue;
+
+        if (steps == 0 || (targetSample >= wps->wphdr.block_index && targetSample < (wps->wphdr.block_index + (i64)wps->wphdr.block_samples))) {
+            i64 index = targetSample - wps->wphdr.block_index;
+            infile->pos = wps->wphdr.stream_position;
+            /* WavpackContext c = WavpackOpenFileInput(infile); wpc.stream = c.stream;
+             * c shares the caller's stream object (position included) and owns a fresh read_buffer, config and error state,
+             * all of which are dropped: only its WavpackStream survives */
+            rd_context *c = (rd_context *)malloc(sizeof(rd_context));
+            ctx_init(c, infile->data, (size_t)infile->len);
+            c->infile.pos = infile->pos;
+            if (setjmp(c->jb)) { /* an exception inside the nested open leaves seek() uncaught */
+                infile->pos = c->infile.pos;
+                rd_close(c);
+                return -2;
+            }
+            open_input(c, 0);
+            infile->pos = c->infile.pos;
+            stream_release(&wpc->stream);
+            wpc->stream = c->stream;
+            ctx_release_rest(c);
+            i32 temp_buf[RD_SAMPLE_BUFFER_SIZE];
+            while (index > 0) {
+                i64 toUnpack = index < RD_SAMPLE_BUFFER_SIZE / rd_get_reduced_channels(wpc) ? index : RD_SAMPLE_BUFFER_SIZE / rd_get_reduced_channels(wpc);
+                toUnpack = rd_unpack_samples(wpc, temp_buf, RD_SAMPLE_BUFFER_SIZE, (long)toUnpack);
+                if (toUnpack == -2) return -2;
+                if (toUnpack == 0) return -3;
+                index -= toUnpack;
+            }
+            return 1;
+        }
+
+        if (seek_pos == -1) {
+            infile->pos = wps->wphdr.stream_position + (i64)wps->wphdr.ckSize;
+            steps--; /* sic: "do not account forward seek by headers" decrements once more */
+        }
+    }
+    return 0;
+}
+
+int rd_set_sample(rd_context *wpc, long sample) /* WavPackUtils.cs:509-512 */
+{
+    return seek_impl(wpc, (i64)sample);
+}
+
+int rd_set_time(rd_context *wpc, long milliseconds) /* WavPackUtils.cs:504-507 */
+{
+    return seek_impl(wpc, (i64)milliseconds / 1000 * wpc->config.sample_rate);
 }
 
 int rd_format_samples(const int32_t *src, long samcnt, int bps, uint8_t *pcm, long pcm_len, int offset, int dsd) /* WavPackUtils.cs:288-341 */

@@ -40,6 +40,11 @@ void rd_close(rd_context *c);
  * have thrown (IndexOutOfRange / EndOfStream) out of the call. */
 long rd_unpack_samples(rd_context *c, int32_t *buffer, long buffer_len, long samples);
 
+/* WavPackUtils.cs:504-594  SetSample / SetTime -> seek().  1 / 0 like the C# bool; -2 where the C# code would throw out
+ * of the call; -3 where it would loop forever (WavpackUnpackSamples returning 0 inside the skip loop). */
+int rd_set_sample(rd_context *c, long sample);
+int rd_set_time(rd_context *c, long milliseconds);
+
 /* WavPackUtils.cs:288 (static, context-free). returns 1/0 like the C# bool. */
 int rd_format_samples(const int32_t *src, long samcnt, int bps, uint8_t *pcm, long pcm_len, int offset, int dsd);
 

@@ -320,3 +320,18 @@ def oracle_wvdemo(data):
         if n >= 0:
             return out[:n].tobytes(), code.value
         cap *= 4
+
+
+class EmulDecoder:
+    """Stand-in for wavpackdecoder_b200.batch.BatchDecoder backed by the host-compiled device code (tests/emul).
+    TEST SEAM ONLY: CPU tests of the API mirror's window / seek logic install it as `wpc._dec`; the product never does."""
+
+    def __init__(self):
+        self.lib = emul()
+
+    def decode(self, in_ptr, in_bytes, descs, nblocks, out_ptr, out_bytes, out_format, mem_flags=0, results=None):
+        assert mem_flags == 0
+        self.lib.emul_decode(in_ptr, descs, nblocks, out_ptr, out_format, results)
+
+    def close(self):
+        pass

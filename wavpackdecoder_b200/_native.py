@@ -30,8 +30,14 @@ class BlockDesc(C.Structure):
         ("int32_info", C.c_uint8 * 4), ("float_info", C.c_uint8 * 4), ("bflags", C.c_uint32), ("version", C.c_uint16),
         ("out_channels", C.c_uint8), ("out_stride", C.c_uint8), ("out_ch_offset", C.c_uint8), ("out_bps", C.c_uint8),
         ("smem_words", C.c_uint16), ("chunk_first", C.c_uint32), ("chunk_samples", C.c_uint32), ("file_id", C.c_uint32),
-        ("gap_before", C.c_uint32), ("terms_sig", C.c_uint32),
+        ("gap_before", C.c_uint32), ("terms_sig", C.c_uint32), ("skip_samples", C.c_uint32), ("skip_chunk", C.c_uint32),
+        ("avg_block_size", C.c_uint32), ("reserved", C.c_uint32),
     ]
+
+
+class SeekState(C.Structure):
+    _fields_ = [("hdr_pos", C.c_int64), ("block_index", C.c_int64), ("avg_block_size", C.c_int64), ("file_pos", C.c_int64),
+                ("block_samples", C.c_uint32), ("ck_size", C.c_uint32)]
 
 
 class BlockResult(C.Structure):
@@ -50,12 +56,12 @@ class FileInfo(C.Structure):
     ]
 
 
-assert C.sizeof(BlockDesc) == 144, C.sizeof(BlockDesc)
+assert C.sizeof(BlockDesc) == 160, C.sizeof(BlockDesc)
 assert C.sizeof(BlockResult) == 16
 
 # every symbol include/wvb.h declares; tests/test_abi.py checks the built library exports all of them
 EXPORTS = [
-    "wvb_abi_version", "wvb_last_error", "wvb_device_count", "wvb_index", "wvb_index_many", "wvb_rebase", "wvb_frame_bytes",
+    "wvb_abi_version", "wvb_abi_layout", "wvb_last_error", "wvb_device_count", "wvb_index", "wvb_index_seek", "wvb_index_many", "wvb_rebase", "wvb_frame_bytes",
     "wvb_batch_create", "wvb_batch_destroy", "wvb_batch_prepare", "wvb_batch_decode", "wvb_batch_wait", "wvb_batch_timing", "wvb_batch_stream",
     "wvb_host_alloc", "wvb_host_free", "wvb_batch_md5", "wvb_stored_md5",
 ]
@@ -66,6 +72,10 @@ def declare_index_api(lib):
     lib.wvb_index.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.POINTER(FileInfo), C.POINTER(BlockDesc),
                               C.c_size_t, C.POINTER(C.c_size_t)]
     lib.wvb_index.restype = C.c_int
+    lib.wvb_index_seek.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.POINTER(SeekState), C.c_int64, C.c_uint32, C.c_uint32, C.c_size_t,
+                                   C.POINTER(FileInfo), C.POINTER(BlockDesc), C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int64),
+                                   C.POINTER(C.c_int64)]
+    lib.wvb_index_seek.restype = C.c_int
     lib.wvb_index_many.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
                                    C.POINTER(FileInfo), C.POINTER(BlockDesc), C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]
@@ -76,7 +86,24 @@ def declare_index_api(lib):
     lib.wvb_frame_bytes.restype = C.c_uint32
     lib.wvb_stored_md5.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
     lib.wvb_stored_md5.restype = C.c_int
+    lib.wvb_abi_layout.restype = C.c_char_p
     return lib
+
+
+def check_layout(lib):
+    """The ctypes mirrors above against the layouts the library was compiled with (wvb_abi_layout)."""
+    mirrors = {"wvb_block_desc": BlockDesc, "wvb_block_result": BlockResult, "wvb_file_info": FileInfo, "wvb_seek_state": SeekState}
+    for part in lib.wvb_abi_layout().decode().split("|"):
+        items = [x for x in part.split(";") if x]
+        name, size = items[0].split(":")
+        cls = mirrors[name]
+        if C.sizeof(cls) != int(size):
+            raise RuntimeError("%s: ctypes mirror is %d bytes, library says %s" % (name, C.sizeof(cls), size))
+        for it in items[1:]:
+            f, off, sz = it.split(":")
+            d = getattr(cls, f)
+            if d.offset != int(off) or d.size != int(sz):
+                raise RuntimeError("%s.%s: ctypes mirror at %d (%d bytes), library says %s (%s bytes)" % (name, f, d.offset, d.size, off, sz))
 
 
 _lib = None
@@ -117,7 +144,8 @@ def load():
     lib.wvb_host_alloc.restype = C.c_void_p
     lib.wvb_host_free.argtypes = [C.c_void_p]
     lib.wvb_host_free.restype = None
-    if lib.wvb_abi_version() != 1:
+    if lib.wvb_abi_version() != 2:
         raise RuntimeError("libwvb.so ABI version mismatch")
+    check_layout(lib)
     _lib = lib
     return lib

@@ -233,15 +233,13 @@ static __global__ void k_dsd_mute_fix(const wvb_block_desc *__restrict__ descs, 
     const wvb_block_desc &D = descs[bi];
     const int unit = out_format == WVB_OUT_INT32 ? 4 : 1, add = out_format == WVB_OUT_PCM ? 128 : 0;
     const uint32_t frame_bytes = (uint32_t)unit * D.out_stride;
-    const uint32_t n = D.block_samples, chunk = D.chunk_samples ? D.chunk_samples : 0xffffffffu;
-    uint32_t first_len = D.chunk_first < n ? D.chunk_first : n;
-    if (first_len == 0) first_len = chunk < n ? chunk : n;
+    const uint32_t n = D.block_samples;
     uint32_t ps = R.mute_from;
     while (ps < n) {
-        const uint32_t pe = ps < first_len ? first_len : (ps + chunk < n ? ps + chunk : n);
+        uint32_t p0, pe;
+        piece_of(D, n, ps, p0, pe);
         // the fill starts at index 0 of the caller's buffer for that call, not at the piece (quirk C-11)
-        int64_t start = ps;
-        if (ps == 0 && D.chunk_first != 0 && D.chunk_first < chunk) start = -(int64_t)(chunk - D.chunk_first);
+        const int64_t start = (int64_t)ps - (int64_t)call_lookback(D, ps);
         uint8_t *q = out + D.out_offset + start * (int64_t)frame_bytes;
         for (uint32_t k = 0; k < pe - ps; ++k, q += frame_bytes)
             for (int c = 0; c < D.out_stride; ++c) store_unit(q + c * unit, 0x55, unit, add);

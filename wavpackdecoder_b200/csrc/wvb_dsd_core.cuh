@@ -86,19 +86,16 @@ WVB_DEV void dsd_finish(const wvb_block_desc &D, wvb_block_result *res, int crc,
 {
     uint32_t rf = extra_flags;
     const uint32_t n = D.block_samples;
-    const uint32_t chunk = D.chunk_samples ? D.chunk_samples : 0xffffffffu;
-    // piece (one unpack_dsd_samples call) that contains sample s
-    uint32_t first_len = D.chunk_first < n ? D.chunk_first : n;
-    if (first_len == 0) first_len = chunk < n ? chunk : n;
-    uint32_t mute_from = n;
+    uint32_t mute_from = n, pe;
     if (failed) { // decode_fast/decode_high returned 0 (DsdUtils.cs:85-91): that piece and all later ones are 0x55
-        if (fail_sample < first_len) mute_from = 0;
-        else mute_from = first_len + ((fail_sample - first_len) / chunk) * chunk;
+        piece_of(D, n, fail_sample < n ? fail_sample : (n ? n - 1 : 0), mute_from, pe);
+        if (n == 0) mute_from = 0;
         rf |= WVB_RF_MUTED | WVB_RF_CRC_ERROR;
         // a failing first piece that starts mid-call leaves partially decoded bytes + stale caller data behind (quirk C-11)
-        if (mute_from == 0 && D.chunk_first != 0 && D.chunk_first < chunk) rf |= WVB_RF_INEXACT;
+        if (call_lookback(D, mute_from)) rf |= WVB_RF_INEXACT;
     } else if (crc != D.crc) { // DsdUtils.cs:99-101: only the last piece is muted
-        mute_from = n <= first_len ? 0 : first_len + ((n - 1 - first_len) / chunk) * chunk;
+        mute_from = 0;
+        if (n) piece_of(D, n, n - 1, mute_from, pe);
         rf |= WVB_RF_MUTED | WVB_RF_CRC_ERROR;
     }
     res->crc = crc;

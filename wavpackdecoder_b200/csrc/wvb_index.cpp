@@ -11,8 +11,11 @@
 // would decode, in output order.
 #include <algorithm>
 #include <atomic>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -37,6 +40,7 @@ struct Header { // WavpackHeader.cs:15-22
     uint32_t block_samples = 0, flags = 0;
     int32_t crc = 0;
     size_t pos = 0; // stream_position
+    int64_t avg = 0; // average_block_size (WavPackUtils.cs:647-650), folded over every header this reader accepted
 };
 
 struct Ctx { // the parts of WavpackContext/WavpackStream the index pass must carry between blocks
@@ -88,6 +92,7 @@ bool read_next_header(Ctx &c)
             h.flags = le32(b + 24);
             h.crc = (int32_t)le32(b + 28);
             h.pos = p;
+            h.avg = h.avg == 0 ? (int64_t)h.ckSize : (h.avg + (int64_t)h.ckSize) / 2;
             c.pos = p + 32;
             return true;
         }
@@ -466,22 +471,36 @@ struct Sink {
     }
 };
 
-// Reference-faithful sequencing: emulates repeated WavpackUnpackSamples(chunk) calls until one returns 0.
-void index_reference_order(Ctx &c, uint32_t chunk, Sink &out)
+// Reference-faithful sequencing: emulates repeated WavpackUnpackSamples calls until one returns 0.
+// Call sizes: `chunk` samples, after an optional prologue of seek()'s skip calls (WavPackUtils.cs:573-578): skip_total
+// samples consumed in calls of at most skip_chunk.  max_blocks > 0 ends the walk after that many descriptors.
+void index_reference_order(Ctx &c, uint32_t chunk, Sink &out, int64_t skip_total = 0, uint32_t skip_chunk = 0, size_t max_blocks = 0)
 {
     wvb_file_info &I = *c.info;
     const int out_ch = I.reduced_channels > 0 ? I.reduced_channels : I.num_channels;
     int64_t out_pos = 0;          // complete samples emitted so far
     int64_t call_remaining = 0;   // samples the current call may still return
     int64_t call_unpacked = 0;
+    int64_t skip_left = skip_total; // samples seek()'s skip loop still has to consume (`index`), kept current sample by sample
+    bool skip_call = false;       // the current call is one of seek()'s
     bool inited = true;           // the block in c.hdr went through unpack_init (true right after open)
     uint32_t pending_gap = 0;
     bool first_iter = true;
+    auto begin_call = [&]() {
+        skip_call = skip_left > 0;
+        call_remaining = skip_call ? std::min<int64_t>(skip_left, skip_chunk ? skip_chunk : chunk) : (int64_t)chunk;
+        call_unpacked = 0;
+    };
     for (;;) {
+        if (max_blocks && out.n >= max_blocks) break;
         if (call_remaining == 0) {
-            if (!first_iter && call_unpacked == 0) break; // the caller stops on a call that returned 0 (WvDemo.cs:133)
-            call_remaining = chunk;
-            call_unpacked = 0;
+            if (!first_iter) {
+                if (call_unpacked == 0) { // the caller stops on a call that returned 0 (WvDemo.cs:133); seek() would spin forever
+                    if (skip_call) I.stopped_early = 1;
+                    break;
+                }
+            }
+            begin_call();
         }
         first_iter = false;
         Header &h = c.hdr;
@@ -500,7 +519,7 @@ void index_reference_order(Ctx &c, uint32_t chunk, Sink &out)
         }
         if (brk) {
             if (c.exception) { I.stopped_early = 1; break; }
-            if (call_unpacked == 0) break;
+            if (call_unpacked == 0) { if (skip_call) I.stopped_early = 1; break; }
             call_remaining = 0; // this call returns short; the caller calls again
             continue;
         }
@@ -511,6 +530,7 @@ void index_reference_order(Ctx &c, uint32_t chunk, Sink &out)
             c.sample_index += n;
             call_unpacked += n;
             call_remaining -= n;
+            if (skip_call) skip_left -= n;
             pending_gap += (uint32_t)n;
             out_pos += n;
             continue;
@@ -531,7 +551,17 @@ void index_reference_order(Ctx &c, uint32_t chunk, Sink &out)
         B.out_offset = (uint64_t)out_pos;
         B.gap_before = pending_gap;
         pending_gap = 0;
-        B.chunk_first = (uint32_t)std::min<int64_t>(call_remaining, 0xffffffffLL);
+        if (skip_call) { // a block seek() decodes and discards (part of): skip calls consume its head, the caller's grid begins after them
+            const uint32_t sc = skip_chunk ? skip_chunk : chunk;
+            B.skip_samples = (uint32_t)std::min<int64_t>(skip_left, n_block);
+            B.skip_chunk = sc;
+            B.chunk_first = chunk;
+            // the descriptor's skip grid starts at the block's first sample; a block entered in the middle of a skip call
+            // (only after a probe sequence that ran out several blocks early) is cut differently by the reference: flagged
+            if (call_remaining != std::min<int64_t>(skip_left, sc)) B.bflags |= WVB_BF_STALE_STATE;
+        } else
+            B.chunk_first = (uint32_t)std::min<int64_t>(call_remaining, 0xffffffffLL);
+        B.avg_block_size = (uint32_t)std::min<int64_t>(h.avg, 0xffffffffLL);
         B.chunk_samples = chunk;
         const bool mono_block = (h.flags & F_MONO) != 0;
         B.out_channels = (uint8_t)(mono_block ? 1 : 2);
@@ -547,9 +577,10 @@ void index_reference_order(Ctx &c, uint32_t chunk, Sink &out)
         out.push(B);
         int64_t left = n_block;
         while (left > 0) {
-            if (call_remaining == 0) { call_remaining = chunk; call_unpacked = 0; }
+            if (call_remaining == 0) begin_call();
             int64_t n = std::min(left, call_remaining);
             left -= n; call_remaining -= n; call_unpacked += n;
+            if (skip_call) skip_left -= n;
         }
         c.sample_index += n_block;
         out_pos += n_block;
@@ -590,7 +621,50 @@ void index_all_channels(Ctx &c, uint32_t chunk, Sink &out)
 
 } // namespace
 
+// ---- layout pins: the hand-written mirrors (ctypes in _native.py, [StructLayout] in csharp/WavPackUtils.cs) depend on these
+static_assert(sizeof(wvb_block_desc) == 160 && alignof(wvb_block_desc) == 8, "wvb_block_desc layout is part of the ABI");
+static_assert(sizeof(wvb_block_result) == 16, "wvb_block_result layout is part of the ABI");
+static_assert(sizeof(wvb_seek_state) == 40, "wvb_seek_state layout is part of the ABI");
+static_assert(sizeof(wvb_file_info) == 224, "wvb_file_info layout is part of the ABI");
+static_assert(offsetof(wvb_block_desc, sub_off) == 40 && offsetof(wvb_block_desc, int32_info) == 104 && offsetof(wvb_block_desc, chunk_first) == 124 &&
+              offsetof(wvb_block_desc, skip_samples) == 144, "wvb_block_desc layout is part of the ABI");
+
 extern "C" {
+
+const char *wvb_abi_layout(void)
+{
+    static std::string text;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        auto add = [&](const char *name, size_t off, size_t size) { text += std::string(name) + ":" + std::to_string(off) + ":" + std::to_string(size) + ";"; };
+#define S(T) text += std::string(text.empty() ? "" : "|") + #T + ":" + std::to_string(sizeof(T)) + ";"
+#define F(T, f) add(#f, offsetof(T, f), sizeof(((T *)0)->f))
+        S(wvb_block_desc);
+        F(wvb_block_desc, in_offset); F(wvb_block_desc, out_offset); F(wvb_block_desc, in_bytes); F(wvb_block_desc, block_samples);
+        F(wvb_block_desc, flags); F(wvb_block_desc, crc); F(wvb_block_desc, block_index); F(wvb_block_desc, sub_off); F(wvb_block_desc, sub_len);
+        F(wvb_block_desc, int32_info); F(wvb_block_desc, float_info); F(wvb_block_desc, bflags); F(wvb_block_desc, version);
+        F(wvb_block_desc, out_channels); F(wvb_block_desc, out_stride); F(wvb_block_desc, out_ch_offset); F(wvb_block_desc, out_bps);
+        F(wvb_block_desc, smem_words); F(wvb_block_desc, chunk_first); F(wvb_block_desc, chunk_samples); F(wvb_block_desc, file_id);
+        F(wvb_block_desc, gap_before); F(wvb_block_desc, terms_sig); F(wvb_block_desc, skip_samples); F(wvb_block_desc, skip_chunk);
+        F(wvb_block_desc, avg_block_size); F(wvb_block_desc, reserved);
+        S(wvb_block_result);
+        F(wvb_block_result, crc); F(wvb_block_result, rflags); F(wvb_block_result, mute_from); F(wvb_block_result, crc_x);
+        S(wvb_file_info);
+        F(wvb_file_info, status); F(wvb_file_info, error_message); F(wvb_file_info, total_samples); F(wvb_file_info, sample_rate);
+        F(wvb_file_info, config_flags); F(wvb_file_info, channel_mask); F(wvb_file_info, num_channels); F(wvb_file_info, reduced_channels);
+        F(wvb_file_info, bits_per_sample); F(wvb_file_info, bytes_per_sample); F(wvb_file_info, float_norm_exp); F(wvb_file_info, xmode);
+        F(wvb_file_info, version); F(wvb_file_info, five); F(wvb_file_info, file_format); F(wvb_file_info, lossy_blocks);
+        F(wvb_file_info, dsd_multiplier); F(wvb_file_info, first_flags); F(wvb_file_info, header_off); F(wvb_file_info, header_len);
+        F(wvb_file_info, trailer_off); F(wvb_file_info, trailer_len); F(wvb_file_info, file_extension); F(wvb_file_info, num_blocks);
+        F(wvb_file_info, indexed_samples); F(wvb_file_info, stopped_early); F(wvb_file_info, reserved);
+        S(wvb_seek_state);
+        F(wvb_seek_state, hdr_pos); F(wvb_seek_state, block_index); F(wvb_seek_state, avg_block_size); F(wvb_seek_state, file_pos);
+        F(wvb_seek_state, block_samples); F(wvb_seek_state, ck_size);
+#undef S
+#undef F
+    });
+    return text.c_str();
+}
 
 int wvb_index(const uint8_t *file, size_t len, uint32_t open_flags, uint32_t chunk_samples, wvb_file_info *info,
               wvb_block_desc *blocks, size_t cap, size_t *nblocks)
@@ -625,6 +699,110 @@ int wvb_index(const uint8_t *file, size_t len, uint32_t open_flags, uint32_t chu
     else index_reference_order(c, chunk_samples, sink);
     info->num_blocks = (int64_t)sink.n;
     if (nblocks) *nblocks = sink.n;
+    if (sink.overflow) return WVB_E_CAPACITY;
+    return WVB_OK;
+}
+
+// seek() (WavPackUtils.cs:521-594): where does the reference restart its decoder?  Replays its probe sequence on the headers
+// (from != NULL) or hops from header to header (from == NULL).  Returns false where seek() returns false.
+static bool seek_find_block(const uint8_t *file, size_t len, const wvb_seek_state *from, int64_t target, size_t *block_pos, int64_t *index)
+{
+    Ctx r;
+    wvb_file_info scratch;
+    r.d = file; r.len = len; r.info = &scratch;
+    if (!from) {
+        while (read_next_header(r)) {
+            const Header &h = r.hdr;
+            if (h.block_samples != 0 && target >= h.block_index && target < h.block_index + (int64_t)h.block_samples) {
+                *block_pos = h.pos;
+                *index = target - h.block_index;
+                return true;
+            }
+            r.pos = std::min<size_t>(len, std::max<size_t>(h.pos + (size_t)h.ckSize + 8, h.pos + 32));
+        }
+        return false;
+    }
+    Header &h = r.hdr;
+    h.pos = (size_t)from->hdr_pos; h.block_index = from->block_index; h.block_samples = from->block_samples; h.ckSize = from->ck_size;
+    h.avg = from->avg_block_size;
+    r.pos = (size_t)std::min<int64_t>(std::max<int64_t>(from->file_pos, 0), (int64_t)len);
+    int steps = 25;     // "maximum steps to position"
+    const int near_blocks = 5; // closer than this: walk the headers forward instead of jumping
+    while (steps-- > 0) {
+        int64_t seek_pos = (int64_t)h.pos;
+        if (target <= (int64_t)h.block_samples)
+            seek_pos = 0;
+        else if (target < h.block_index || target > h.block_index + (int64_t)h.block_samples) {
+            int64_t distance = target - h.block_index;
+            distance += distance > 0 ? 1 - (int64_t)h.block_samples : 1 - 2 * (int64_t)h.block_samples; // back-off so that the walk ends going forward
+            if (h.block_samples == 0) return false; // the reference divides by zero here (uncaught): no seek either way
+            const int64_t blocks = distance / (int64_t)h.block_samples;
+            if (blocks >= 0 && blocks <= near_blocks) seek_pos = -1;
+            else seek_pos += blocks * h.avg;
+            if (seek_pos >= (int64_t)len) seek_pos = -1;
+        }
+        if (seek_pos != -1) {
+            if (seek_pos < 0) return false; // Stream.Seek before the start: IOException, caught, `return false`
+            r.pos = (size_t)seek_pos;
+        }
+        if (!read_next_header(r)) continue; // wphdr.error: the step is spent, the header fields stay
+        if (steps == 0 || (target >= h.block_index && target < h.block_index + (int64_t)h.block_samples)) {
+            *block_pos = h.pos;
+            *index = target - h.block_index;
+            return true;
+        }
+        if (seek_pos == -1) {
+            r.pos = std::min<size_t>(len, h.pos + (size_t)h.ckSize);
+            steps--; // the reference means to not count header walks and decrements once more instead
+        }
+    }
+    return false;
+}
+
+int wvb_index_seek(const uint8_t *file, size_t len, uint32_t open_flags, const wvb_seek_state *from, int64_t target, uint32_t skip_chunk,
+                   uint32_t chunk_samples, size_t max_blocks, wvb_file_info *info, wvb_block_desc *blocks, size_t cap, size_t *nblocks,
+                   int64_t *window_first_sample, int64_t *landed_sample)
+{
+    if (!file || !info) return WVB_E_ARG;
+    if (open_flags & WVB_OPEN_ALL_CHANNELS) return WVB_E_ARG; // the extension has its own order; seek it by block_index in the full table
+    if (chunk_samples == 0) chunk_samples = 4096;
+    if (nblocks) *nblocks = 0;
+    if (window_first_sample) *window_first_sample = 0;
+    if (landed_sample) *landed_sample = 0;
+    size_t n_all = 0;
+    int rc = wvb_index(file, len, open_flags, chunk_samples, info, nullptr, 0, &n_all); // the file as WavpackOpenFileInput sees it
+    if (rc != WVB_OK || info->status != WVB_OK) return rc;
+    info->num_blocks = 0;
+    info->indexed_samples = 0;
+    info->stopped_early = 0;
+    if (target >= info->total_samples) return WVB_OK;   // WavPackUtils.cs:527-528 (also: unknown length, total_samples == -1)
+    if (target < 0) target = 0;                         // WavPackUtils.cs:529-530
+    size_t block_pos = 0;
+    int64_t index = 0;
+    if (!seek_find_block(file, len, from, target, &block_pos, &index)) return WVB_OK;
+    // `WavpackContext c = WavpackOpenFileInput(infile); wpc.stream = c.stream;` (WavPackUtils.cs:568-570): a fresh stream state
+    // at that block; the nested context's config is dropped, the caller's (info) stays
+    wvb_file_info scratch = *info;
+    Ctx c;
+    c.d = file; c.len = len; c.info = &scratch;
+    c.pos = block_pos;
+    memset(&c.cur, 0, sizeof(c.cur));
+    while (c.hdr.block_samples == 0) {
+        if (!read_next_header(c)) return WVB_OK;
+        if (!unpack_init(c)) { info->stopped_early = 1; return WVB_OK; }
+    }
+    const int out_ch = info->reduced_channels > 0 ? info->reduced_channels : (info->num_channels ? info->num_channels : 2);
+    if (skip_chunk == 0) skip_chunk = (uint32_t)(4096 / out_ch); // Defines.SAMPLE_BUFFER_SIZE / WavpackGetReducedChannels
+    const int64_t first = c.sample_index; // the restarted decoder's position: the block's block_index
+    Sink sink{blocks, cap};
+    index_reference_order(c, chunk_samples, sink, std::max<int64_t>(index, 0), skip_chunk, max_blocks);
+    info->num_blocks = (int64_t)sink.n;
+    info->indexed_samples = scratch.indexed_samples;
+    info->stopped_early = scratch.stopped_early;
+    info->lossy_blocks |= scratch.lossy_blocks;
+    if (nblocks) *nblocks = sink.n;
+    if (window_first_sample) *window_first_sample = first;
+    if (landed_sample) *landed_sample = first + std::max<int64_t>(index, 0); // index <= 0: nothing is skipped, the reader stands at the block's start
     if (sink.overflow) return WVB_E_CAPACITY;
     return WVB_OK;
 }

@@ -17,6 +17,7 @@
 
 #include "../../include/wvb.h"
 #include "wv_tables.h"
+#include "wvb_grid.h"
 
 #ifdef __CUDACC__
 #define WVB_DEV __device__ __forceinline__
@@ -777,17 +778,9 @@ struct OutWriter {
 };
 
 // The reference decodes a block in caller-sized pieces (one unpack_samples call each).  piece_bounds() recovers the piece
-// [ps, pe) that contains sample t from the descriptor's chunk grid; it is evaluated only at piece events and on faults, so
-// the grid costs one register (the next event) in the sample loop.
-WVB_DEV void piece_bounds(const wvb_block_desc &D, uint32_t n, uint32_t t, uint32_t &ps, uint32_t &pe)
-{
-    const uint32_t chunk = D.chunk_samples ? D.chunk_samples : 0xffffffffu;
-    uint32_t first = D.chunk_first < n ? D.chunk_first : n;
-    if (first == 0) first = chunk < n ? chunk : n;
-    if (t < first) { ps = 0; pe = first; return; }
-    ps = first + ((t - first) / chunk) * chunk;
-    pe = (n - ps) < chunk ? n : ps + chunk;
-}
+// [ps, pe) that contains sample t from the descriptor's call grid (wvb_grid.h); it is evaluated only at piece events and on
+// faults, so the grid costs one register (the next event) in the sample loop.
+WVB_DEV void piece_bounds(const wvb_block_desc &D, uint32_t n, uint32_t t, uint32_t &ps, uint32_t &pe) { piece_of(D, n, t, ps, pe); }
 // next sample index at which the weights are cast to short: 8 samples into a stereo piece of >= 16 samples, and the piece end
 template <bool STEREO> WVB_DEV uint32_t next_piece_event(uint32_t t, uint32_t ps, uint32_t pe)
 {

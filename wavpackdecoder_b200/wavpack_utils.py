@@ -11,9 +11,10 @@ one to one:
 Differences that are deliberate:
   * the stream is an in-memory bytes-like object (the reference takes a BinaryReader): the batch decoder needs the
     whole compressed file to ship it to the GPU;
-  * the first WavpackUnpackSamples call decodes the WHOLE file on the device (every block in parallel) and later calls
-    copy out of that result; the chunk size of the first call fixes the reference's chunk-dependent behaviour on
-    corrupt streams (muting granularity), exactly as if every call used that size;
+  * WavpackUnpackSamples decodes a WINDOW of blocks on the device -- every block from the one that contains the current
+    position on, all in parallel -- and later calls copy out of it; a seek (SetSample / SetTime) or a call with a different
+    size starts a new window at the containing block, with the call grid the reference would have used (the grid decides
+    mute granularity and short-weight casts on damaged streams);
   * there is no CPU fallback: without libwvb.so / a CUDA device the unpack call raises.
 No decode arithmetic lives here: Python only slices buffers and forwards getters.
 """
@@ -41,23 +42,35 @@ class WavpackContext:
     def __init__(self):
         self.data = None
         self.info = None
-        self.descs = None
-        self.nblocks = 0
         self.error_message = None
         self.crc_errors = 0
         self.sample_index = 0
         self.open_flags = 0
         self.device = 0
-        self._decoded = None      # int32 samples of the whole file, interleaved
-        self._results = None
-        self._block_ends = None   # cumulative sample positions at which each block's CRC verdict becomes visible
-        self._chunk = None
+        self.lookahead_blocks = 0   # blocks decoded per device pass from the current position; 0 = to the end of the file
+        self.decode_passes = 0      # device passes made so far (a streaming caller sees 1; every seek or chunk-size change adds one)
         self._out_channels = 0
+        self._win = None            # the decoded window (_Table with .decoded)
+        self._pending = None        # block table made by SetSample / SetTime, decoded by the next WavpackUnpackSamples
+        self._dec = None
+
+    def __del__(self):
+        try:
+            if self._dec is not None:
+                self._dec.close()
+        except Exception:
+            pass
+
+
+class _Table:
+    """Block table of a window: the block decoding (re)starts at and the ones after it."""
+    __slots__ = ("descs", "nblocks", "first", "landed", "nsamples", "chunk", "origin", "starts", "ends", "hdr", "decoded", "crc_flags",
+                 "next_pos", "stopped_early", "lossy_blocks")
 
 
 def WavpackOpenFileInput(infile, flags=0, device=0):
     """WavPackUtils.cs:36-120.  `infile`: bytes-like with the .wv stream.  Never raises for format errors: check
-    WavpackGetErrorMessage(), like the reference."""
+    WavpackGetErrorMessage(), like the reference.  Host work only (the block-header walk); nothing is decoded yet."""
     lib = N.load()
     wpc = WavpackContext()
     wpc.data = np.frombuffer(infile, dtype=np.uint8)
@@ -76,56 +89,155 @@ def WavpackOpenFileInput(infile, flags=0, device=0):
     return wpc
 
 
-def _decode_all(wpc, chunk):
-    """Index with the caller's chunk size and decode every block on the device (int32 output)."""
+def _make_table(wpc, chunk, origin, target=0, max_blocks=0):
+    """Index pass for one window.  origin: ("open",) -- the table WavpackOpenFileInput + sequential reads produce;
+    ("seek", wvb_seek_state or None) -- after the reference's seek() to `target`; ("regrid", previous call size) -- the caller
+    went on reading at `target` with another call size (no seek: the block's consumed head was cut in the previous size)."""
     lib = N.load()
-    from .batch import BatchDecoder
+    d, size = wpc.data.ctypes.data, wpc.data.size
     info = N.FileInfo()
     n = C.c_size_t()
-    lib.wvb_index(wpc.data.ctypes.data, wpc.data.size, wpc.open_flags, chunk, C.byref(info), None, 0, C.byref(n))
-    descs = (N.BlockDesc * max(n.value, 1))()
-    lib.wvb_index(wpc.data.ctypes.data, wpc.data.size, wpc.open_flags, chunk, C.byref(info), descs, n.value, C.byref(n))
-    nblocks = n.value
-    lib.wvb_rebase(descs, nblocks, 0, 0, N.OUT_INT32, 0)
+    first, landed = C.c_int64(0), C.c_int64(0)
+
+    def call(descs, cap):
+        if origin[0] == "open":
+            rc = lib.wvb_index(d, size, wpc.open_flags, chunk, C.byref(info), descs, cap, C.byref(n))
+            if rc == N.E_CAPACITY and max_blocks:
+                rc = N.OK  # only the head of the table was asked for
+            return rc
+        state = C.byref(origin[1]) if origin[0] == "seek" and origin[1] is not None else None
+        skip_chunk = origin[1] if origin[0] == "regrid" else 0
+        return lib.wvb_index_seek(d, size, wpc.open_flags, state, target, skip_chunk, chunk, max_blocks, C.byref(info), descs, cap,
+                                  C.byref(n), C.byref(first), C.byref(landed))
+
+    if origin[0] == "open" and max_blocks:
+        n.value = max_blocks
+    elif call(None, 0) != N.OK:
+        raise RuntimeError("block index failed")
+    t = _Table()
+    t.nblocks = n.value
+    t.descs = (N.BlockDesc * max(t.nblocks, 1))()
+    if t.nblocks and call(t.descs, t.nblocks) != N.OK:
+        raise RuntimeError("block index failed")
+    t.nblocks = min(t.nblocks, n.value)
+    t.first, t.landed = first.value, landed.value
+    t.chunk, t.origin = chunk, origin
+    t.nsamples = int(info.indexed_samples) if t.nblocks else 0
+    t.stopped_early, t.lossy_blocks = bool(info.stopped_early), info.lossy_blocks
+    # per block: first / last+1 sample in the file, and what the reference's reader remembers of its header
+    t.starts = np.array([t.first + int(t.descs[i].out_offset) for i in range(t.nblocks)], dtype=np.int64)
+    t.ends = np.array([t.first + int(t.descs[i].out_offset) + int(t.descs[i].block_samples) for i in range(t.nblocks)], dtype=np.int64)
+    t.hdr = [(int(b.in_offset), int(b.block_index), int(b.block_samples), int(b.in_bytes), int(b.avg_block_size)) for b in t.descs[:t.nblocks]]
+    if origin[0] == "open" and max_blocks and t.nblocks:
+        t.nsamples = int(t.ends[-1] - t.first)  # only the head of the whole-file table was kept
+    t.decoded = None
+    t.next_pos = t.landed if origin[0] != "open" else 0
+    return t
+
+
+def _reader_state(wpc):
+    """What the reference's reader holds when seek() starts: the header it read last (the block of the last sample handed
+    out, or the block decoding (re)started at) and the file position behind that block."""
+    tab = wpc._pending or wpc._win
+    if tab is None:
+        tab = _make_table(wpc, SAMPLE_BUFFER_SIZE, ("open",), max_blocks=1)
+    if tab.nblocks == 0:
+        return None
+    before = np.nonzero(tab.starts < wpc.sample_index)[0]
+    j = int(before[-1]) if before.size else 0
+    pos, block_index, block_samples, in_bytes, avg = tab.hdr[j]
+    return N.SeekState(hdr_pos=pos, block_index=block_index, avg_block_size=avg, file_pos=pos + in_bytes, block_samples=block_samples,
+                       ck_size=max(in_bytes - 8, 0))
+
+
+def _decode_table(wpc, t):
+    """One device pass over a window's blocks, all in parallel."""
+    lib = N.load()
+    from .batch import BatchDecoder
     nch = wpc._out_channels
-    out = np.zeros(int(info.indexed_samples) * nch + 16, dtype=np.int32)
-    results = (N.BlockResult * max(nblocks, 1))()
-    slab = np.concatenate([wpc.data, np.zeros(64, dtype=np.uint8)])
-    dec = BatchDecoder(wpc.device)  # raises without a CUDA device: no fallback
-    try:
-        dec.decode(slab.ctypes.data, slab.size, descs, nblocks, out.ctypes.data, int(info.indexed_samples) * nch * 4, N.OUT_INT32, 0, results)
-    finally:
-        dec.close()
-    wpc._decoded = out[: int(info.indexed_samples) * nch]
-    wpc._results = [results[i] for i in range(nblocks)]
-    wpc._block_ends = [int(descs[i].out_offset // (4 * nch)) + int(descs[i].block_samples) for i in range(nblocks)]
-    wpc.descs, wpc.nblocks, wpc._chunk = descs, nblocks, chunk
-    wpc.info.lossy_blocks = info.lossy_blocks
+    if t.nblocks:
+        lib.wvb_rebase(t.descs, t.nblocks, 0, 0, N.OUT_INT32, 0)
+        out = np.zeros(t.nsamples * nch + 16, dtype=np.int32)
+        results = (N.BlockResult * t.nblocks)()
+        slab = np.concatenate([wpc.data, np.zeros(64, dtype=np.uint8)])
+        if wpc._dec is None:
+            wpc._dec = BatchDecoder(wpc.device)  # raises without a CUDA device: no fallback
+        wpc._dec.decode(slab.ctypes.data, slab.size, t.descs, t.nblocks, out.ctypes.data, t.nsamples * nch * 4, N.OUT_INT32, 0, results)
+        wpc.decode_passes += 1
+        t.decoded = out[: t.nsamples * nch]
+        t.crc_flags = np.array([bool(results[i].rflags & N.RF_CRC_ERROR) for i in range(t.nblocks)], dtype=bool)
+        wpc.info.lossy_blocks |= t.lossy_blocks
+    else:
+        t.decoded = np.zeros(0, dtype=np.int32)
+        t.crc_flags = np.zeros(0, dtype=bool)
+    wpc._win = t
+    wpc._pending = None
+
+
+def _new_window(wpc, chunk):
+    win, pend = wpc._win, wpc._pending
+    if pend is not None:  # after SetSample / SetTime
+        t = pend if pend.chunk == chunk and pend.origin[0] == "seek" and not wpc.lookahead_blocks else \
+            _make_table(wpc, chunk, pend.origin, pend.origin[2] if len(pend.origin) > 2 else wpc.sample_index, wpc.lookahead_blocks)
+    elif win is None and wpc.sample_index == 0:
+        t = _make_table(wpc, chunk, ("open",), max_blocks=wpc.lookahead_blocks)
+    elif wpc.info.total_samples < 0:
+        # unknown length: the reference cannot seek such files (WavPackUtils.cs:527) and neither can the index; a call-size
+        # change mid-stream re-reads from the start with the new size
+        t = _make_table(wpc, chunk, ("open",))
+    else:
+        prev = win.chunk if win is not None and win.next_pos == wpc.sample_index else 0
+        t = _make_table(wpc, chunk, ("regrid", prev) if prev else ("seek", None), wpc.sample_index, wpc.lookahead_blocks)
+    # a seek that starts by decoding an earlier block (see wvb_index_seek) counts that block's CRC verdict when the skip loop
+    # finishes it (WavPackUtils.cs:273-275 inside the skip calls)
+    _decode_table(wpc, t)
+    if t.origin[0] == "seek" and t.nblocks:
+        wpc.crc_errors += int(np.count_nonzero(t.crc_flags & (t.ends <= wpc.sample_index)))
+    t.next_pos = wpc.sample_index
 
 
 def WavpackUnpackSamples(wpc, buffer, samples):
     """WavPackUtils.cs:200-282: fills `buffer` (numpy int32, >= samples * channels) with right-justified samples and
-    returns the number of complete samples unpacked (short at end of stream)."""
+    returns the number of complete samples unpacked (short at end of stream).
+
+    The first call decodes every block from the current position on in ONE device pass (the whole file for a caller that
+    starts at 0; `wpc.lookahead_blocks` bounds it) and later calls copy out of that window.  The call size is part of the
+    reference's behaviour on damaged streams (mute granularity, short-weight casts): a call with another size, or after
+    SetSample / SetTime, decodes a new window from the block that contains the current position.  With a bounded
+    lookahead the call grid restarts at every window (exact for undamaged streams)."""
     if wpc.error_message:
         return 0
-    if wpc._decoded is None:
-        _decode_all(wpc, int(samples))
-    nch = wpc._out_channels
-    total = wpc._decoded.size // nch
-    n = int(min(samples, total - wpc.sample_index))
-    if wpc.info.total_samples >= 0 and wpc.sample_index < wpc.info.total_samples:
-        n = int(min(n, wpc.info.total_samples - wpc.sample_index))  # the call returns at total_samples (WavPackUtils.cs:277)
-    if n <= 0:
+    samples = int(samples)
+    if samples <= 0:
         return 0
-    a = wpc.sample_index * nch
-    buffer[: n * nch] = wpc._decoded[a: a + n * nch]
-    new_index = wpc.sample_index + n
-    # crc_errors becomes visible when the block's last sample has been handed out (WavPackUtils.cs:273-275)
-    for end, r in zip(wpc._block_ends, wpc._results):
-        if wpc.sample_index < end <= new_index and (r.rflags & N.RF_CRC_ERROR):
-            wpc.crc_errors += 1
-    wpc.sample_index = new_index
-    return n
+    nch = wpc._out_channels
+    win = wpc._win
+    if win is None or wpc._pending is not None or win.chunk != samples or win.next_pos != wpc.sample_index:
+        _new_window(wpc, samples)
+        win = wpc._win
+    done = 0
+    while done < samples:
+        n = int(min(samples - done, win.first + win.nsamples - wpc.sample_index))
+        if wpc.info.total_samples >= 0 and wpc.sample_index < wpc.info.total_samples:
+            n = int(min(n, wpc.info.total_samples - wpc.sample_index))  # the call returns at total_samples (WavPackUtils.cs:277)
+        if n <= 0:
+            if wpc.lookahead_blocks and win.nblocks >= wpc.lookahead_blocks:  # a full window: the stream may go on
+                _new_window(wpc, samples)
+                win = wpc._win
+                if win.nsamples and wpc.sample_index < win.first + win.nsamples:
+                    continue
+            break
+        a = (wpc.sample_index - win.first) * nch
+        buffer[done * nch: (done + n) * nch] = win.decoded[a: a + n * nch]
+        new_index = wpc.sample_index + n
+        # crc_errors becomes visible when the block's last sample has been handed out (WavPackUtils.cs:273-275)
+        wpc.crc_errors += int(np.count_nonzero(win.crc_flags & (win.ends > wpc.sample_index) & (win.ends <= new_index)))
+        wpc.sample_index = new_index
+        win.next_pos = new_index
+        done += n
+        if new_index == wpc.info.total_samples:
+            break
+    return done
 
 
 def WavpackFormatSamples(src, samcnt, bps, pcm_buffer, offset=0, dsd=False):
@@ -267,13 +379,23 @@ def WavpackGetCompressionLevel(wpc):  # WavPackUtils.cs:169-187
 
 
 def SetSample(wpc, sample):
-    """WavPackUtils.cs:509-594 replaced by an O(1) move over the block index: the whole file is decoded
-    once, so seeking is repositioning.  Returns False past the end, like the reference."""
-    if wpc.info.total_samples >= 0 and sample >= wpc.info.total_samples:
+    """WavPackUtils.cs:509-594.  The reference probes the file for the block that contains `sample` (up to 25 header reads
+    steered by the average block size), restarts its decoder there and decodes-and-discards up to the target.  Here the
+    index pass replays that probe sequence on the headers (wvb_index_seek; host work, no decoding) and the next
+    WavpackUnpackSamples decodes from the block it ends on, the discarded head included, with the same call grid -- one
+    device pass over the blocks from there on, not over the whole file.
+    Returns False where the reference does: past the end of the stream, streams of unknown length, failed probes."""
+    sample = int(sample)
+    if sample >= wpc.info.total_samples or wpc.error_message:
         return False
-    wpc.sample_index = max(0, int(sample))
+    t = _make_table(wpc, wpc._win.chunk if wpc._win is not None else SAMPLE_BUFFER_SIZE, ("seek", _reader_state(wpc), sample), sample,
+                    wpc.lookahead_blocks)
+    if t.nblocks == 0:
+        return False
+    wpc._pending = t
+    wpc.sample_index = t.landed
     return True
 
 
 def SetTime(wpc, milliseconds):  # WavPackUtils.cs:504-507
-    return SetSample(wpc, milliseconds // 1000 * int(wpc.info.sample_rate))
+    return SetSample(wpc, int(milliseconds) // 1000 * int(wpc.info.sample_rate))

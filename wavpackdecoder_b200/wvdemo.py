@@ -117,7 +117,7 @@ def unpack_files(files, device=0, reference_quirks=True):
     return res
 
 
-C_DESC_WORDS = 144 // 8
+C_DESC_WORDS = 160 // 8
 
 
 def main(argv=None):
