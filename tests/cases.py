@@ -102,6 +102,11 @@ DSD_CASES = [
     ("dsd3_stereo", 0, 4096, dict(kind=KIND_DSD, dsd_mode=3, seconds=0.1, block_samples=8192)),
     ("dsd3_rate200", 0, 4096, dict(kind=KIND_DSD, dsd_mode=3, dsd_rate_i=200, seconds=0.1, block_samples=5000)),
     ("dsd3_extras", 0, 4096, dict(kind=KIND_DSD, dsd_mode=3, seconds=0.1, block_samples=8192, extras=2 | 4 | 8 | 16)),
+    # raw-mode blocks whose payload and output start at every kind of misalignment, shorter than one vector step, and long
+    ("dsd0_mono_odd_blocks", 0, 4096, dict(kind=KIND_DSD, dsd_mode=0, channels=1, seconds=0.1, block_samples=5001)),
+    ("dsd0_stereo_odd_blocks", 0, 4096, dict(kind=KIND_DSD, dsd_mode=0, seconds=0.1, block_samples=4099, extras=2 | 4)),
+    ("dsd0_mono_tiny_blocks", 0, 4096, dict(kind=KIND_DSD, dsd_mode=0, channels=1, seconds=0.002, block_samples=37)),
+    ("dsd0_stereo_big_blocks", 0, 4096, dict(kind=KIND_DSD, dsd_mode=0, seconds=0.2, block_samples=44100)),
 ]
 
 

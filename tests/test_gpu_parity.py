@@ -1,4 +1,5 @@
 """GPU parity proper: the CUDA path through the C ABI (libwvb.so) against the oracle, bit exact."""
+import ctypes as C
 import hashlib
 import json
 import os
@@ -218,7 +219,7 @@ def test_packed_pcm_at_unaligned_output_offsets(gpu, kw):
     try:
         for shift in (0, 1, 2, 3, 5):
             corpus = Corpus.from_files([bytes(data)], out_format=gpu.OUT_PCM)
-            table = np.frombuffer(corpus.descs, dtype=np.uint64).reshape(-1, 18)
+            table = np.frombuffer(corpus.descs, dtype=np.uint64).reshape(-1, C.sizeof(gpu.BlockDesc) // 8)
             table[:corpus.nblocks, 1] += shift  # out_offset
             total = corpus.out_bytes + shift + 7
             d_out = torch.full((total + 64,), 0xEE, dtype=torch.uint8, device="cuda")

@@ -57,6 +57,25 @@ class FileInfo(C.Structure):
 
 
 assert C.sizeof(BlockDesc) == 160, C.sizeof(BlockDesc)
+
+
+def desc_table(descs, n):
+    """numpy structured view (no copy) of a ctypes BlockDesc array: host-side bookkeeping over 10^5 descriptors
+    (shard costs, per-file error counts) without a Python loop."""
+    import numpy as np
+    dt = np.dtype([("in_offset", "<u8"), ("out_offset", "<u8"), ("in_bytes", "<u4"), ("block_samples", "<u4"), ("flags", "<u4"), ("crc", "<i4"),
+                   ("block_index", "<i8"), ("sub_off", "<u4", (8,)), ("sub_len", "<u4", (8,)), ("int32_info", "u1", (4,)), ("float_info", "u1", (4,)),
+                   ("bflags", "<u4"), ("version", "<u2"), ("out_channels", "u1"), ("out_stride", "u1"), ("out_ch_offset", "u1"), ("out_bps", "u1"),
+                   ("smem_words", "<u2"), ("chunk_first", "<u4"), ("chunk_samples", "<u4"), ("file_id", "<u4"), ("gap_before", "<u4"),
+                   ("terms_sig", "<u4"), ("skip_samples", "<u4"), ("skip_chunk", "<u4"), ("avg_block_size", "<u4"), ("reserved", "<u4")])
+    assert dt.itemsize == C.sizeof(BlockDesc)
+    return np.frombuffer(descs, dtype=dt, count=n)
+
+
+def result_table(results, n):
+    import numpy as np
+    dt = np.dtype([("crc", "<i4"), ("rflags", "<u4"), ("mute_from", "<u4"), ("crc_x", "<i4")])
+    return np.frombuffer(results, dtype=dt, count=n)
 assert C.sizeof(BlockResult) == 16
 
 # every symbol include/wvb.h declares; tests/test_abi.py checks the built library exports all of them

@@ -146,20 +146,65 @@ class BatchDecoder:
         return out, results
 
 
-def decode_files(files, open_flags=0, chunk_samples=4096, out_format=N.OUT_INT32, device=0):
-    """Convenience: decode a list of .wv byte strings; returns list of (numpy array, crc_errors, info)."""
-    corpus = Corpus.from_files(files, open_flags=open_flags, chunk_samples=chunk_samples, out_format=out_format)
-    dec = BatchDecoder(device)
-    try:
-        out, results = dec.decode_corpus(corpus)
-    finally:
-        dec.close()
+def _file_results(corpus, out, results):
+    t = N.result_table(results, corpus.nblocks)
+    crc_err = np.concatenate([[0], np.cumsum((t["rflags"] & N.RF_CRC_ERROR) != 0)])
     res = []
     for i in range(corpus.nfiles):
         f, c = int(corpus.first[i]), int(corpus.count[i])
-        errs = sum(1 for k in range(f, f + c) if results[k].rflags & N.RF_CRC_ERROR)
-        res.append((corpus.file_output(out, i).copy(), errs, corpus.infos[i], [results[k] for k in range(f, f + c)]))
+        res.append((corpus.file_output(out, i).copy(), int(crc_err[f + c] - crc_err[f]), corpus.infos[i], [results[k] for k in range(f, f + c)]))
     return res
+
+
+def decode_files(files, open_flags=0, chunk_samples=4096, out_format=N.OUT_INT32, device=0, devices=None):
+    """Decode a list of .wv byte strings; returns a list of (numpy array, crc_errors, info, block results) in file order.
+
+    devices: a list of CUDA device ordinals shards ONE batch by file over several GPUs of the box: the files are
+    indexed once, cut into contiguous ranges of equal decode cost (sharding.shard_contiguous_by_cost over
+    sum(block_samples x passes)), and every device decodes its range on its own host thread and wvb_batch; shards share
+    nothing, the only gather is the per-file results on the host.  No collective is involved."""
+    if devices is None or len(devices) <= 1:
+        corpus = Corpus.from_files(files, open_flags=open_flags, chunk_samples=chunk_samples, out_format=out_format)
+        dec = BatchDecoder(devices[0] if devices else device)
+        try:
+            out, results = dec.decode_corpus(corpus)
+        finally:
+            dec.close()
+        return _file_results(corpus, out, results)
+    import threading
+    from .sharding import file_costs, shard_contiguous_by_cost
+    whole = Corpus.from_files(files, open_flags=open_flags, chunk_samples=chunk_samples, out_format=out_format)
+    ranges = shard_contiguous_by_cost(file_costs(whole), len(devices))
+    parts, errors = [None] * len(devices), []
+
+    def work(k):
+        lo, hi = ranges[k]
+        if hi <= lo:
+            parts[k] = []
+            return
+        try:
+            # the shard's files are adjacent in the slab: a view of it, offsets rebased, is its own corpus (no copy)
+            base = int(whole.offsets[lo])
+            end = int(whole.offsets[hi - 1]) + int(whole.sizes[hi - 1])
+            sub = Corpus(whole.slab[base:min(whole.slab.size, end + 64)], whole.offsets[lo:hi] - np.uint64(base), whole.sizes[lo:hi],
+                         open_flags=open_flags, chunk_samples=chunk_samples, out_format=out_format)
+            dec = BatchDecoder(devices[k])
+            try:
+                out, results = dec.decode_corpus(sub)
+            finally:
+                dec.close()
+            parts[k] = _file_results(sub, out, results)
+        except Exception as e:  # surfaced on the calling thread
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(devices))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return [r for p in parts for r in p]
 
 
 def stored_md5(data):

@@ -56,14 +56,15 @@ struct SharedColumn { // word i of this thread's column; [slot][thread] layout
 template <bool STEREO, bool HYB, bool GENFIX, class DEC, int MINB = 0, bool F16 = false>
 __global__ void __launch_bounds__(CTA_THREADS, MINB)
 k_decode_pcm(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ descs, const uint32_t *__restrict__ order,
-             uint32_t count, uint8_t *__restrict__ out, int out_format, wvb_block_result *__restrict__ results)
+             uint32_t count, uint8_t *__restrict__ out, int out_format, wvb_block_result *__restrict__ results, int one)
 {
     extern __shared__ int smem[];
     const uint32_t i = blockIdx.x * CTA_THREADS + threadIdx.x;
     const bool valid = i < count; // lanes past the end keep running (with no work): the decode loop is warp-synchronous
     const uint32_t bi = order[valid ? i : count - 1];
     SharedColumn SM{smem + threadIdx.x};
-    wvb::decode_block_pcm<STEREO, HYB, GENFIX, SharedColumn, DEC, F16>(SM, in, descs[bi], out, out_format, &results[bi], valid);
+    // `one`: the constant 1 as a kernel parameter, i.e. a constant-bank operand the compiler cannot fold (wvb_pcm.cuh: addc)
+    wvb::decode_block_pcm<STEREO, HYB, GENFIX, SharedColumn, DEC, F16>(SM, in, descs[bi], out, out_format, &results[bi], valid, one);
 }
 
 using GenS = wvb::GenericDecorr<true>;
@@ -117,7 +118,7 @@ template <class T> int ensure(T *&p, size_t &cap, size_t need)
     return WVB_OK;
 }
 
-typedef void (*pcm_kernel_t)(const uint8_t *, const wvb_block_desc *, const uint32_t *, uint32_t, uint8_t *, int, wvb_block_result *);
+typedef void (*pcm_kernel_t)(const uint8_t *, const wvb_block_desc *, const uint32_t *, uint32_t, uint8_t *, int, wvb_block_result *, int);
 
 pcm_kernel_t pcm_kernel(int variant, uint32_t count = 0, int sm_count = 148)
 {
@@ -178,6 +179,11 @@ void make_plan(const wvb_block_desc *descs, size_t n, int fmt, std::vector<uint3
         const uint64_t inv_len = 0x3fffffffu - (d.block_samples < 0x3fffffffu ? d.block_samples : 0x3fffffffu);
         key[i] = ((uint64_t)v << 56) | (clsbits << 46) | ((uint64_t)(d.terms_sig & 0xffff) << 30) | inv_len;
     }
+    // Ties keep the table's order, i.e. neighbouring blocks of the same files share a warp: their compressed streams and
+    // their outputs lie next to each other in the slabs.  (Measured and rejected in round 2: ordering ties by compressed
+    // size so that silent stretches -- zero-run mode, which 64 % of the warp iterations execute for the sake of one lane --
+    // get warps of their own.  The bench launch went from 77 to 150 ms: every lane of a warp then streams from a different
+    // 2 MB page of the slabs and the TLBs thrash.)
     std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key[a] != key[b] ? key[a] < key[b] : a < b; });
     launches.clear();
     size_t i = 0;
@@ -375,7 +381,7 @@ static int launch_plan(wvb_batch *b, const std::vector<Launch> &plan, const uint
         if (smem > b->smem_optin) return set_error(WVB_E_ARG, "shared memory class exceeds the device limit");
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         unsigned grid = (L.count + CTA_THREADS - 1) / CTA_THREADS;
-        k<<<grid, CTA_THREADS, smem, s>>>(din, b->d_descs, b->d_order + L.first, L.count, dout, fmt == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : fmt, dres);
+        k<<<grid, CTA_THREADS, smem, s>>>(din, b->d_descs, b->d_order + L.first, L.count, dout, fmt == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : fmt, dres, 1);
         CUDA_TRY(cudaGetLastError());
         b->launches++;
     }

@@ -41,6 +41,25 @@ static __device__ __forceinline__ uint32_t pow3(uint32_t e)
     return r;
 }
 
+// 16 source bytes starting `mis` bytes into the 32 bytes (a, b): the copy is store-aligned, so the loads are whatever the
+// block's position in the file makes them (warp-uniform misalignment: every lane is 16 bytes from its neighbour)
+static __device__ __forceinline__ uint4 dsd_extract16(const uint4 a, const uint4 b, uint32_t mis)
+{
+    uint32_t w0 = a.x, w1 = a.y, w2 = a.z, w3 = a.w, w4 = b.x;
+    const uint32_t idx = mis >> 2;
+    if (idx == 1) { w0 = a.y; w1 = a.z; w2 = a.w; w3 = b.x; w4 = b.y; }
+    else if (idx == 2) { w0 = a.z; w1 = a.w; w2 = b.x; w3 = b.y; w4 = b.z; }
+    else if (idx == 3) { w0 = a.w; w1 = b.x; w2 = b.y; w3 = b.z; w4 = b.w; }
+    const uint32_t sh = 8u * (mis & 3u);
+    return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+}
+// crc*3+byte over the 16 bytes of v, starting from 0: sum b_i * 3^(15-i).  One byte dot product per word (27,9,3,1).
+static __device__ __forceinline__ uint32_t dsd_crc16(const uint4 v)
+{
+    const uint32_t k = 0x0103091bu; // byte 0 (first in memory) x 27, byte 1 x 9, byte 2 x 3, byte 3 x 1
+    return ((__dp4a(v.x, k, 0u) * 81u + __dp4a(v.y, k, 0u)) * 81u + __dp4a(v.z, k, 0u)) * 81u + __dp4a(v.w, k, 0u);
+}
+
 static __global__ void __launch_bounds__(DSD_RAW_THREADS)
 k_dsd_raw(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ descs, const uint32_t *__restrict__ order, uint32_t count,
           uint8_t *__restrict__ out, int out_format, wvb_block_result *__restrict__ results)
@@ -57,23 +76,84 @@ k_dsd_raw(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ des
     const uint32_t len = D.sub_len[WVB_SUB_DSD];
     uint32_t total = D.block_samples * (uint32_t)o.coded_ch;
     if (len - 2 < total) total = len - 2; // DsdUtils.cs:77-78
-    const uint32_t lane_pow = pow3(124u - 4u * (uint32_t)lane), step_pow = pow3(128u);
     uint32_t crc = 0xffffffffu;
-    const uint32_t full = total & ~127u;
-    // fast path: plain byte output of a stereo (or mono) stream into a contiguous frame layout
+    // plain byte output of a stereo (or mono) stream into a contiguous frame layout: a copy
     const bool bytes_contig = o.unit == 1 && o.frame_bytes == (uint32_t)o.coded_ch && o.out_ch == o.coded_ch;
+    if (bytes_contig) {
+        // The tile-movement kernel of the path: 16-byte aligned vector stores, 16-byte aligned vector loads realigned in
+        // registers, and the CRC as one byte dot product per word.  A warp step moves 512 bytes; the CRC of a step is
+        // crc*3^512 + sum over lanes of crc16(lane) * 3^(16*(31-lane)), one warp reduction.
+        uint8_t *dst = o.op;
+        uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);
+        if (head > total) head = total;
+        for (uint32_t j = 0; j < head; ++j) { // (every lane walks the few head bytes: the CRC stays warp-uniform)
+            const uint32_t b = p[j];
+            crc = crc * 3u + b;
+            if (lane == 0) dst[j] = (uint8_t)(b + (uint32_t)o.add);
+        }
+        const uint8_t *src = p + head;
+        dst += head;
+        const uint32_t body = total - head, nchunks = body >> 4;
+        const uint32_t mis = (uint32_t)((uintptr_t)src & 15u);
+        const uint4 *sa = (const uint4 *)(src - mis);
+        uint4 *da = (uint4 *)dst;
+        const uint32_t flip = o.add ? 0x80808080u : 0u; // +128 per byte
+        const uint32_t lane_pow = pow3(16u * (31u - (uint32_t)lane)), step_pow = pow3(512u);
+        uint32_t c = 0;
+        const uint32_t FULL = 0xffffffffu;
+        for (; c + 64 <= nchunks; c += 64) { // two warp steps per trip: both loads are in flight before the first is used
+            const uint4 a0 = __ldg(sa + c + lane), a1 = __ldg(sa + c + 32 + lane);
+            uint4 e = make_uint4(0, 0, 0, 0);
+            if (lane == 31 && mis) e = __ldg(sa + c + 64); // (mis == 0 never looks past its own 16 bytes: no read beyond the payload)
+            // the 16 bytes after a lane's own: the next lane's; for lane 31 the first lane's of the next step
+            uint4 b0 = make_uint4(__shfl_down_sync(FULL, a0.x, 1), __shfl_down_sync(FULL, a0.y, 1), __shfl_down_sync(FULL, a0.z, 1), __shfl_down_sync(FULL, a0.w, 1));
+            uint4 b1 = make_uint4(__shfl_down_sync(FULL, a1.x, 1), __shfl_down_sync(FULL, a1.y, 1), __shfl_down_sync(FULL, a1.z, 1), __shfl_down_sync(FULL, a1.w, 1));
+            const uint4 f1 = make_uint4(__shfl_sync(FULL, a1.x, 0), __shfl_sync(FULL, a1.y, 0), __shfl_sync(FULL, a1.z, 0), __shfl_sync(FULL, a1.w, 0));
+            if (lane == 31) { b0 = f1; b1 = e; }
+            const uint4 v0 = dsd_extract16(a0, b0, mis), v1 = dsd_extract16(a1, b1, mis);
+            crc = crc * step_pow + __reduce_add_sync(FULL, dsd_crc16(v0) * lane_pow);
+            crc = crc * step_pow + __reduce_add_sync(FULL, dsd_crc16(v1) * lane_pow);
+            __stcs(da + c + lane, make_uint4(v0.x ^ flip, v0.y ^ flip, v0.z ^ flip, v0.w ^ flip));
+            __stcs(da + c + 32 + lane, make_uint4(v1.x ^ flip, v1.y ^ flip, v1.z ^ flip, v1.w ^ flip));
+        }
+        for (; c + 32 <= nchunks; c += 32) {
+            const uint4 a = __ldg(sa + c + lane);
+            uint4 b = make_uint4(__shfl_down_sync(FULL, a.x, 1), __shfl_down_sync(FULL, a.y, 1), __shfl_down_sync(FULL, a.z, 1), __shfl_down_sync(FULL, a.w, 1));
+            if (lane == 31 && mis) b = __ldg(sa + c + 32);
+            const uint4 v = dsd_extract16(a, b, mis);
+            crc = crc * step_pow + __reduce_add_sync(FULL, dsd_crc16(v) * lane_pow);
+            __stcs(da + c + lane, make_uint4(v.x ^ flip, v.y ^ flip, v.z ^ flip, v.w ^ flip));
+        }
+        const uint32_t rest = nchunks - c; // a last, partial warp step
+        if (rest) {
+            const bool mine = (uint32_t)lane < rest;
+            uint4 a = make_uint4(0, 0, 0, 0), b = a;
+            if (mine) {
+                a = __ldg(sa + c + lane);
+                if (mis) b = __ldg(sa + c + lane + 1);
+            }
+            const uint4 v = dsd_extract16(a, b, mis);
+            const uint32_t term = mine ? dsd_crc16(v) * pow3(16u * (rest - 1u - (uint32_t)lane)) : 0u;
+            crc = crc * pow3(16u * rest) + __reduce_add_sync(0xffffffffu, term);
+            if (mine) __stcs(da + c + lane, make_uint4(v.x ^ flip, v.y ^ flip, v.z ^ flip, v.w ^ flip));
+        }
+        for (uint32_t j = head + (nchunks << 4); j < total; ++j) { // fewer than 16 bytes
+            const uint32_t b = p[j];
+            crc = crc * 3u + b;
+            if (lane == 0) o.op[j] = (uint8_t)(b + (uint32_t)o.add);
+        }
+        if (lane == 0) dsd_finish(D, &results[bi], (int)crc, false, 0, 0);
+        return;
+    }
+    // any other layout (int32 output, FALSE_STEREO duplication, channel slots inside wider frames): 4 values per lane and step
+    const uint32_t lane_pow = pow3(124u - 4u * (uint32_t)lane), step_pow = pow3(128u);
+    const uint32_t full = total & ~127u;
     for (uint32_t base = 0; base < full; base += 128) {
         const uint32_t j = base + 4u * (uint32_t)lane;
         const uint32_t b0 = p[j], b1 = p[j + 1], b2 = p[j + 2], b3 = p[j + 3];
         const uint32_t local = ((b0 * 3u + b1) * 3u + b2) * 3u + b3;
         crc = crc * step_pow + __reduce_add_sync(0xffffffffu, local * lane_pow);
-        if (bytes_contig) {
-            uint8_t *q = o.op + j;
-            const uint32_t a = (uint32_t)o.add;
-            q[0] = (uint8_t)(b0 + a); q[1] = (uint8_t)(b1 + a); q[2] = (uint8_t)(b2 + a); q[3] = (uint8_t)(b3 + a);
-        } else {
-            o.put(j, (int)b0); o.put(j + 1, (int)b1); o.put(j + 2, (int)b2); o.put(j + 3, (int)b3);
-        }
+        o.put(j, (int)b0); o.put(j + 1, (int)b1); o.put(j + 2, (int)b2); o.put(j + 3, (int)b3);
     }
     if (lane == 0) { // tail (< 128 values) and the verdict
         for (uint32_t j = full; j < total; ++j) {
