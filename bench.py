@@ -11,7 +11,13 @@ A step = one decode pass over the whole batch.
   value  : decoded complete samples/s, whole job, compressed input and PCM output resident in HBM
   e2e    : same metric through the public C-ABI call with HOST (pinned) buffers: host index pass + H2D of the
            compressed slab + kernels + D2H of the PCM, every step
+  e2e.pcie_ceiling: the same pinned buffers and byte counts moved with no decode (H2D and D2H at once, all ranks at once):
+           the roofline of the end-to-end path; e2e.frac_of_ceiling = e2e / that
   roofline: algorithmic bytes (compressed block bytes in + PCM bytes out) / CUDA-event kernel time vs measured HBM peak
+  configs : the other BASELINE.json configs (1: one 60 s file, the latency case; 3: 24-bit 5.1 with 16 terms; 4: float /
+           int32 / hybrid; 5: DSD64 modes 0/1/3), device-resident, short launches, each validated against the oracle.
+           Under torchrun configs 3 and 5 are ONE logical corpus cut by decode cost over the ranks (strong scaling),
+           per-file results gathered on rank 0
   cpu_baseline: the oracle (C restatement of the reference, one file per thread on all host cores) on a bounded sample
 The C# reference cannot run in this image (no .NET); the reference arm therefore times the C restatement ("port").
 """
@@ -199,6 +205,164 @@ def ncu_traffic():
 
 
 # --------------------------------------------------------------------------------------
+# copy-only ceiling of the end-to-end path
+# --------------------------------------------------------------------------------------
+def pcie_ceiling(slab_t, n_in, out_t, n_out, dev, barrier, max_over_ranks, reps=3):
+    """The step's bytes over PCIe with no decode: H2D of the compressed slab and D2H of the PCM at the same time, from / into
+    the very pinned buffers the e2e leg uses, all ranks at once (barrier before, max over ranks after).  Best of `reps`."""
+    import torch
+    d_in = torch.empty(n_in, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(n_out, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def run(do_in, do_out):
+        best = None
+        for _ in range(reps):
+            barrier()
+            t0 = time.perf_counter()
+            if do_in:
+                with torch.cuda.stream(s1):
+                    d_in.copy_(slab_t[:n_in], non_blocking=True)
+            if do_out:
+                with torch.cuda.stream(s2):
+                    out_t[:n_out].copy_(d_out, non_blocking=True)
+            torch.cuda.synchronize()
+            dt = max_over_ranks(time.perf_counter() - t0, dev)
+            best = dt if best is None else min(best, dt)
+        return best
+
+    run(True, True)
+    both, h2d, d2h = run(True, True), run(True, False), run(False, True)
+    del d_in, d_out
+    return {"both_s": both, "h2d_alone_gbs_per_gpu": n_in / h2d / 1e9, "d2h_alone_gbs_per_gpu": n_out / d2h / 1e9,
+            "d2h_gbs_per_gpu_while_h2d": n_out / both / 1e9}
+
+
+# --------------------------------------------------------------------------------------
+# the other BASELINE configs: short device-resident launches
+# --------------------------------------------------------------------------------------
+T16 = [18, 18, 2, 3, -2, 18, 2, 4, 7, 5, 3, 6, 8, -1, 18, 2]
+# name -> (BASELINE config, encoder kwargs, open flags, files per launch at 1 GPU, seconds per file, sharded under torchrun)
+EXTRA_CONFIGS = [
+    ("config1_one_60s_file", 1, dict(), 0, 1, 60.0, False),
+    ("config3_24bit_51_16terms_2ch_max", 3, dict(bits=24, channels=6, sample_rate=48000, block_samples=24000, terms=T16, deltas=[2] * 16), 0x8, 6000, 5.0, True),
+    ("config3_24bit_51_16terms_all_channels", 3, dict(bits=24, channels=6, sample_rate=48000, block_samples=24000, terms=T16, deltas=[2] * 16), 0x10000, 2000, 5.0, False),
+    ("config4a_float", 4, dict(kind=2, bits=32), 0, 6000, 10.0, False),
+    ("config4b_int32_wvx", 4, dict(bits=32, int32_sent_bits=8), 0, 6000, 10.0, False),
+    ("config4c_hybrid_stereo", 4, dict(kind=1), 0, 8000, 10.0, False),
+    ("config4c_hybrid_mono", 4, dict(kind=1, channels=1, terms=[18, 18, 2, 3], deltas=[2, 2, 2, 2]), 0, 12000, 10.0, False),
+    ("config5_dsd64_raw", 5, dict(kind=3, dsd_mode=0, block_samples=22050), 0, 1000, 10.0, True),
+    ("config5_dsd64_fast", 5, dict(kind=3, dsd_mode=1, block_samples=22050), 0, 1000, 10.0, True),
+    ("config5_dsd64_high", 5, dict(kind=3, dsd_mode=3, block_samples=22050), 0, 1000, 10.0, True),
+]
+
+
+def unique_files(cfg_kw, seconds, seed, threads, budget_s, want):
+    """Up to `want` unique encoded files within ~budget_s: (slab, offsets, sizes, samples per file)."""
+    c = build_corpus(want, seconds, seed, threads, budget_s, pin=False, cfg_kw=cfg_kw)
+    u = c["unique"]
+    return c["slab"], c["offsets"][:u].copy(), c["sizes"][:u].copy(), c["samples_per_file"]
+
+
+def run_extra_config(name, cfg_kw, open_flags, nfiles, seconds, sharded, args, rank, world, dev, threads, peak, barrier):
+    """One BASELINE config as a device-resident launch.  The logical corpus is `nfiles` files (unique encodes of two
+    durations, replicated); under torchrun a sharded config is cut into contiguous ranges of equal decode cost
+    (wavpackdecoder_b200.sharding) and every rank materialises and decodes its own range."""
+    import torch
+    import torch.distributed as dist
+    import _harness as H
+    from wavpackdecoder_b200 import _native as N
+    from wavpackdecoder_b200.batch import BatchDecoder, Corpus
+    from wavpackdecoder_b200.sharding import file_costs, max_over_ranks, shard_contiguous_by_cost
+    budget = args.config_gen_budget_s
+    want = max(2, min(nfiles, 4000))
+    # two durations, so that the cost-based cut is not the trivial equal split
+    sets = [unique_files(cfg_kw, seconds, 0xC0DE0000, threads, budget * 0.6, want)]
+    if nfiles > 1:
+        sets.append(unique_files(cfg_kw, seconds / 2, 0xC0DE8000, threads, budget * 0.4, want))
+    fmt = N.OUT_PCM
+    set_costs, set_samples = [], []
+    for slab_u, offs_u, sizes_u, _ in sets:
+        cu = Corpus(slab_u, offs_u, sizes_u, open_flags=open_flags, out_format=fmt, threads=threads)
+        assert all(cu.infos[i].status == 0 for i in range(cu.nfiles)), name
+        set_costs.append(file_costs(cu))
+        set_samples.append(np.array([int(cu.infos[i].indexed_samples) for i in range(cu.nfiles)], dtype=np.int64))
+    ids = np.arange(nfiles)
+    which = (ids % 3 == 2).astype(np.int64) if len(sets) > 1 else np.zeros(nfiles, dtype=np.int64)  # every third file is a short one
+    uid = np.where(which == 0, ids % len(set_costs[0]), ids % len(set_costs[-1]))
+    costs = np.where(which == 0, set_costs[0][uid % len(set_costs[0])], set_costs[-1][uid % len(set_costs[-1])])
+    w = world if sharded else 1
+    lo, hi = shard_contiguous_by_cost(costs, w)[rank if sharded else 0]
+    # materialise this rank's range
+    sizes = np.array([int(sets[which[i]][2][uid[i]]) for i in range(lo, hi)], dtype=np.uint64)
+    offsets = np.zeros(hi - lo, dtype=np.uint64)
+    pos = 0
+    for k in range(hi - lo):
+        offsets[k] = pos
+        pos += (int(sizes[k]) + 63) & ~63
+    slab = np.zeros(pos + 64, dtype=np.uint8)
+    for k, i in enumerate(range(lo, hi)):
+        sl, so, ss, _ = sets[which[i]]
+        o = int(so[uid[i]])
+        slab[int(offsets[k]):int(offsets[k]) + int(sizes[k])] = sl[o:o + int(sizes[k])]
+    cp = Corpus(slab, offsets, sizes, open_flags=open_flags, out_format=fmt, threads=threads)
+    dec = BatchDecoder(dev.index)
+    try:
+        d_in = torch.from_numpy(slab).to(dev)
+        d_out = torch.empty(cp.out_bytes + 64, dtype=torch.uint8, device=dev)
+        d_res = torch.empty(max(cp.nblocks, 1) * 16, dtype=torch.uint8, device=dev)
+        dec.prepare(cp.descs, cp.nblocks, fmt)
+        FL = N.IN_DEVICE | N.OUT_DEVICE | N.RESULTS_DEVICE
+
+        def step():
+            dec.decode(d_in.data_ptr(), slab.size, None, cp.nblocks, d_out.data_ptr(), cp.out_bytes, fmt, FL, d_res.data_ptr())
+
+        for _ in range(2):
+            step()
+        # validation: every block clean, first and last file of the range byte-identical with the oracle
+        res = d_res.cpu().numpy().view(np.uint32).reshape(-1, 4)[:cp.nblocks]
+        flagged = int((res[:, 1] != 0).sum())
+        ok = flagged == 0
+        for i in sorted({0, cp.nfiles - 1}) if cp.nfiles else []:
+            data = slab[int(offsets[i]):int(offsets[i]) + int(sizes[i])].tobytes()
+            if open_flags & 0x10000:
+                continue  # (the all-channels extension has no whole-file oracle; its blocks are CRC-checked above)
+            ref, errs, status, info = H.oracle_decode(data, open_flags)
+            o = int(cp.file_out_offset[i])
+            got = d_out[o:o + ref.size * info["bytes_per_sample"]].cpu().numpy()
+            ok = ok and status == 0 and errs == 0 and np.array_equal(got, H.format_samples(ref, info["bytes_per_sample"]))
+        kernel_ms = []
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.config_steps):
+            step()
+            kernel_ms.append(dec.timing()["kernel_ms"])
+        torch.cuda.synchronize()
+        elapsed = max_over_ranks(time.perf_counter() - t0, dev) if sharded else time.perf_counter() - t0
+    finally:
+        dec.close()
+    local = np.array([cp.total_samples, cp.nblocks, int(sizes.sum()), cp.out_bytes, flagged, int(ok), hi - lo, float(np.mean(kernel_ms)) * 1e3], dtype=np.int64)
+    if sharded and world > 1:
+        t = torch.from_numpy(local).to(dev)
+        allr = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allr, t)  # per-rank results gathered (rank 0 prints them); the data path itself has no collective
+        allr = torch.stack(allr).cpu().numpy()
+    else:
+        allr = local[None, :]
+    tot = allr.sum(axis=0)
+    k_ms = float(allr[:, 7].max()) / 1e3
+    algo = int(tot[2] + tot[3])
+    out = {"baseline_config": None, "scaling": "strong" if sharded and world > 1 else "single-gpu", "files": int(tot[6]), "blocks": int(tot[1]),
+           "samples": int(tot[0]), "kernel_ms": k_ms, "value": tot[0] * args.config_steps / elapsed, "unit": UNIT,
+           "algorithmic_bytes": algo, "achieved_gbs": algo / (k_ms * 1e-3) / 1e9 / (world if sharded else 1),
+           "validated": bool(tot[5] == allr.shape[0] and tot[4] == 0), "flagged_blocks": int(tot[4])}
+    out["frac"] = out["achieved_gbs"] / peak
+    if sharded and world > 1:
+        out["per_rank"] = [{"files": int(r[6]), "blocks": int(r[1]), "samples": int(r[0]), "kernel_ms": r[7] / 1e3} for r in allr]
+    return out
+
+
+# --------------------------------------------------------------------------------------
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -253,6 +417,10 @@ def main():
     ap.add_argument("--cpu-baseline-s", type=float, default=15.0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` object (the other BASELINE configs)")
+    ap.add_argument("--only-configs", default="", help="comma-separated substrings: run only the matching entries of `configs`")
+    ap.add_argument("--config-steps", type=int, default=3)
+    ap.add_argument("--config-gen-budget-s", type=float, default=6.0)
     args = ap.parse_args()
     if args.warmup < 3:
         log("note: W < 3 requested; the timing rules want >= 3 warm-up steps")
@@ -369,7 +537,7 @@ def main():
             dec.decode(slab.ctypes.data, slab.size, c2.descs, c2.nblocks, out_np.ctypes.data, pcm_bytes, N.OUT_PCM, 0, results)
             return c2
 
-        for _ in range(2):
+        for _ in range(max(args.warmup, 1)):
             step_e2e()
         barrier()
         t0 = time.perf_counter()
@@ -378,10 +546,20 @@ def main():
         torch.cuda.synchronize()
         e_elapsed = time.perf_counter() - t0
         e_elapsed_max = max_over_ranks(e_elapsed, dev)
-        e2e_ok = all((results[i].rflags == 0) for i in range(0, cp.nblocks, max(1, cp.nblocks // 1000)))
-        e2e = {"value": total_samples * world * args.steps / e_elapsed_max, "unit": UNIT,
+        # validation of what came back over PCIe: every block's result clean, and the PCM bytes of three files compared with
+        # the oracle's decode of the same .wv bytes
+        rt = N.result_table(results, cp.nblocks)
+        e2e_ok = bool((rt["rflags"] == 0).all())
+        for i in sorted({0, cp.nfiles // 2, cp.nfiles - 1}):
+            o = int(c2.file_out_offset[i])
+            data = slab[int(corpus["offsets"][i]):int(corpus["offsets"][i]) + int(corpus["sizes"][i])].tobytes()
+            ref, errs, status, info = H.oracle_decode(data)
+            want = H.format_samples(ref, 2)
+            e2e_ok = e2e_ok and status == 0 and errs == 0 and np.array_equal(out_np[o:o + want.size], want)
+        e2e_value = total_samples * world * args.steps / e_elapsed_max
+        e2e = {"value": e2e_value, "unit": UNIT,
                "h2d_bytes_per_step": int(slab.size + cp.nblocks * (160 + 4)), "d2h_bytes_per_step": int(pcm_bytes + cp.nblocks * 16),
-               "includes": "host block-index pass + H2D + kernels + D2H", "validated": bool(e2e_ok)}
+               "includes": "host block-index pass + H2D + kernels + D2H", "validated": bool(e2e_ok), "ms_per_step": 1000.0 * e_elapsed_max / args.steps}
 
     # ---- verify-only end to end: host .wv bytes in, PCM stays in HBM, MD5 per file computed on the device,
     # only 16 B per file and the per-block results come back.  Extra to the contract's `e2e`; same timing rules. ----
@@ -397,7 +575,7 @@ def main():
             lens = np.array([int(c2.infos[i].indexed_samples) * 4 for i in range(c2.nfiles)], dtype=np.uint64)
             return c2, dec.md5_ranges(c2.file_out_offset, lens, pcm_bytes, d_out.data_ptr())
 
-        for _ in range(2):
+        for _ in range(max(args.warmup, 1)):
             step_verify()
         barrier()
         t0 = time.perf_counter()
@@ -416,6 +594,15 @@ def main():
                       "d2h_bytes_per_step": int(c2.nfiles * 16 + cp.nblocks * 16),
                       "includes": "host block-index pass + H2D + kernels + device MD5 per file; PCM never leaves HBM", "validated": bool(v_ok)}
         del d_out
+
+    if e2e is not None:
+        # the e2e leg's own roofline: its bytes over PCIe with no decode (this overwrites the pinned output buffer: last use)
+        ceil = pcie_ceiling(corpus["slab_t"], slab.size, out_t, pcm_bytes, dev, barrier, max_over_ranks)
+        ceil_value = total_samples * world / ceil["both_s"]
+        ceil.update({"value": ceil_value, "unit": UNIT,
+                     "what": "H2D of the compressed slab and D2H of the PCM at once, same pinned buffers, no decode, all ranks at once, best of 3"})
+        e2e["pcie_ceiling"] = ceil
+        e2e["frac_of_ceiling"] = e2e["value"] / ceil_value
 
     # ---- roofline of the dominant kernel ----
     peak, peak_kind = measured_peak()
@@ -439,12 +626,40 @@ def main():
                              "warp_instructions_per_32_samples": traffic["warp_instructions_per_launch"] / total_samples * 32}
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline:  # (the other ranks wait at the next barrier)
         cores = host_cores()
-        n = size_cpu_sample(corpus, cores, args.cpu_baseline_s)
+        n = size_cpu_sample(corpus, cores, args.cpu_baseline_s if world == 1 else args.cpu_baseline_s / 2)
         s, dt = cpu_decode_sample(corpus, n, cores)
         cpu_baseline = {"value": s / dt, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": "%d of the %d files, one file per thread, decode + WavpackFormatSamples, %.1f s" % (n, args.files, dt)}
+    barrier()
+
+    # ---- the other BASELINE configs ----
+    configs = None
+    if not args.no_configs:
+        # release the headline batch's memory first
+        d_in = d_out = d_res = out_t = out_np = None  # noqa: F841
+        dec.close()
+        corpus.pop("slab_t", None)
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        configs = {}
+        wanted = [x for x in args.only_configs.split(",") if x]
+        for name, bcfg, kw, oflags, nfiles, secs, sharded in EXTRA_CONFIGS:
+            if wanted and not any(x in name for x in wanted):
+                continue
+            if world > 1 and not sharded:
+                continue  # at N > 1 only the configs BASELINE.json shards (3 and 5) run, as one corpus cut over the ranks
+            t0 = time.perf_counter()
+            try:
+                r = run_extra_config(name, kw, oflags, nfiles * (world if sharded else 1), secs, sharded, args, rank, world, dev, threads, peak, barrier)
+                r["baseline_config"] = bcfg
+            except Exception as e:  # one failing config must not take the headline line with it
+                r = {"baseline_config": bcfg, "error": repr(e)[:300]}
+                barrier()
+            configs[name] = r
+            log("%s: %s (%.1f s)" % (name, {k: v for k, v in r.items() if k != "per_rank"}, time.perf_counter() - t0))
 
     if rank == 0:
         line = {
@@ -452,7 +667,7 @@ def main():
             "ms_per_step": 1000.0 * elapsed_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic (in-repo encoder, %d unique files per GPU, validated vs oracle: %s)" % (corpus["unique"], validated),
             "config": workload_config(args, corpus, cp.nblocks), "clocks": clk, "e2e": e2e, "gpu_launches": launches,
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e_verify": e2e_verify,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e_verify": e2e_verify, "configs": configs,
             "pcm_gb_per_s": pcm_bytes * world * args.steps / elapsed_max / 1e9, "validated": bool(validated),
         }
         print(json.dumps(line), flush=True)

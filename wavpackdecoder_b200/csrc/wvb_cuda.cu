@@ -56,15 +56,14 @@ struct SharedColumn { // word i of this thread's column; [slot][thread] layout
 template <bool STEREO, bool HYB, bool GENFIX, class DEC, int MINB = 0, bool F16 = false>
 __global__ void __launch_bounds__(CTA_THREADS, MINB)
 k_decode_pcm(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ descs, const uint32_t *__restrict__ order,
-             uint32_t count, uint8_t *__restrict__ out, int out_format, wvb_block_result *__restrict__ results, int one)
+             uint32_t count, uint8_t *__restrict__ out, int out_format, wvb_block_result *__restrict__ results)
 {
     extern __shared__ int smem[];
     const uint32_t i = blockIdx.x * CTA_THREADS + threadIdx.x;
     const bool valid = i < count; // lanes past the end keep running (with no work): the decode loop is warp-synchronous
     const uint32_t bi = order[valid ? i : count - 1];
     SharedColumn SM{smem + threadIdx.x};
-    // `one`: the constant 1 as a kernel parameter, i.e. a constant-bank operand the compiler cannot fold (wvb_pcm.cuh: addc)
-    wvb::decode_block_pcm<STEREO, HYB, GENFIX, SharedColumn, DEC, F16>(SM, in, descs[bi], out, out_format, &results[bi], valid, one);
+    wvb::decode_block_pcm<STEREO, HYB, GENFIX, SharedColumn, DEC, F16>(SM, in, descs[bi], out, out_format, &results[bi], valid);
 }
 
 using GenS = wvb::GenericDecorr<true>;
@@ -118,7 +117,7 @@ template <class T> int ensure(T *&p, size_t &cap, size_t need)
     return WVB_OK;
 }
 
-typedef void (*pcm_kernel_t)(const uint8_t *, const wvb_block_desc *, const uint32_t *, uint32_t, uint8_t *, int, wvb_block_result *, int);
+typedef void (*pcm_kernel_t)(const uint8_t *, const wvb_block_desc *, const uint32_t *, uint32_t, uint8_t *, int, wvb_block_result *);
 
 pcm_kernel_t pcm_kernel(int variant, uint32_t count = 0, int sm_count = 148)
 {
@@ -381,7 +380,7 @@ static int launch_plan(wvb_batch *b, const std::vector<Launch> &plan, const uint
         if (smem > b->smem_optin) return set_error(WVB_E_ARG, "shared memory class exceeds the device limit");
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         unsigned grid = (L.count + CTA_THREADS - 1) / CTA_THREADS;
-        k<<<grid, CTA_THREADS, smem, s>>>(din, b->d_descs, b->d_order + L.first, L.count, dout, fmt == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : fmt, dres, 1);
+        k<<<grid, CTA_THREADS, smem, s>>>(din, b->d_descs, b->d_order + L.first, L.count, dout, fmt == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : fmt, dres);
         CUDA_TRY(cudaGetLastError());
         b->launches++;
     }

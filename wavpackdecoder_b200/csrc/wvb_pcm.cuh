@@ -55,48 +55,6 @@ static inline uint32_t wvb_warp_max(uint32_t v) { return v; }
 
 namespace wvb {
 
-// Integer adds on the FMA pipe.  On sm_100 the ALU pipe (IADD3, LOP3, SHF, SEL, ISETP) and the FMA pipe (IMAD) each issue
-// one warp instruction every two cycles per scheduler, and this decoder is almost all ALU work (ncu, round 2: 263 ALU vs
-// 135 FMA warp instructions per frame, ALU pipe 69 % busy, FMA 27 %).  An add of an immediate has no IMAD encoding
-// (x*1+c needs two immediates), so the compiler must leave it on the ALU; with the 1 in a register it has one.  `one` is the
-// constant 1 in a form the compiler cannot fold (derived from the launch configuration, so it lives in a uniform register).
-#if defined(__CUDACC__) && defined(WVB_FMA_ADDS) && WVB_FMA_ADDS == 2
-// variant 2: the addend comes from constant memory (an operand slot of both IADD3 and IMAD.IADD): the compiler is free to
-// pick the pipe, as it already does for register + register adds
-static __device__ __constant__ int wvb_kc[12] = {1, -1, -2, -32, 30, 32, 62, 64, 126, 128, 0, 0};
-constexpr int kc_index(int c)
-{
-    return c == 1 ? 0 : c == -1 ? 1 : c == -2 ? 2 : c == -32 ? 3 : c == 30 ? 4 : c == 32 ? 5 : c == 62 ? 6 : c == 64 ? 7 : c == 126 ? 8 : c == 128 ? 9 : -1;
-}
-template <int C> WVB_DEV int addk(int x, int)
-{
-    static_assert(kc_index(C) >= 0, "constant not in wvb_kc");
-#ifdef __CUDA_ARCH__
-    return x + wvb_kc[kc_index(C)];
-#else
-    return x + C;
-#endif
-}
-#elif defined(__CUDACC__) && defined(WVB_FMA_ADDS)
-template <int C> WVB_DEV int addk(int x, int one) { return x * one + C; }
-#else
-template <int C> WVB_DEV int addk(int x, int) { return x + C; }
-#endif
-template <int C> WVB_DEV uint32_t addk(uint32_t x, int one) { return (uint32_t)addk<C>((int)x, one); }
-
-// number of significant bits of x (0 for 0): 32 - clz, taken from the MSB index so that no subtraction is needed
-WVB_DEV int bit_length(uint32_t x, int one)
-{
-#if defined(__CUDA_ARCH__) && defined(WVB_FMA_ADDS)
-    int msb;
-    asm("bfind.u32 %0, %1;" : "=r"(msb) : "r"(x)); // -1 for x == 0
-    return addk<1>(msb, one);
-#else
-    (void)one;
-    return 32 - wvb_clz(x);
-#endif
-}
-
 WVB_TABLE uint8_t k_log2[256] = WV_LOG2_TABLE_INIT;
 WVB_TABLE uint8_t k_exp2[256] = WV_EXP2_TABLE_INIT;
 
@@ -146,7 +104,6 @@ struct BitReader {
     uint32_t w0, w1;     // window: bit `pos` of w1:w0 is the next bit of the stream; 64 - pos bits are valid
     uint32_t nw;         // word fetched one refill ahead: its load latency overlaps the decode of the bits before it
     int pos;             // 0..63 (every consumer leaves at least one valid bit or refills first)
-    int one = 1;         // see addk()
 
     WVB_DEV uint32_t load_word()
     {
@@ -195,16 +152,11 @@ struct BitReader {
                          "setp.lt.u32 p, %3, %5;\n\t"
                          "mad.wide.u32 a, %3, 4, %7;\n\t"
                          "@p ld.global.nc.u32 %2, [a];\n\t"
-#ifdef WVB_FMA_ADDS
-                         "mad.lo.u32 %3, %3, %8, 1;\n\t"
-                         "mad.lo.s32 %4, %4, %8, -32;\n\t"
-#else
                          "add.u32 %3, %3, 1;\n\t"
                          "sub.s32 %4, %4, 32;\n\t"
-#endif
                          "}"
                          : "+r"(w0), "+r"(w1), "+r"(nw), "+r"(idx), "+r"(pos)
-                         : "r"(full_end), "r"(tailw), "l"(base), "r"(one));
+                         : "r"(full_end), "r"(tailw), "l"(base));
 #else
             w0 = w1;
             w1 = nw;
@@ -331,9 +283,8 @@ template <bool HYB, bool STEREO, int CH> WVB_DEV bool decode_word(BitReader &br,
         // rarely agree on `ones`, so every branch here would be walked on both sides anyway, plus its (re)convergence cost.
         br.refill();
         const bool held0 = w.hold == 2; // a zero left over from the previous word: no unary prefix (WordsUtils.cs:354-358)
-        const int one = br.one;
-        int nb = wvb_ffs(~br.peek()); // WordsUtils.cs:361-428
-        int t = addk<-1>(nb, one);
+        int t = wvb_ffs(~br.peek()) - 1; // WordsUtils.cs:361-428
+        int nb = t + 1;
         if (!held0 && (unsigned)t >= 16u) { // escape: 16 ones, then a zero and a gamma-coded count, or a 17th one = end of stream
             br.consume(16);
             nb = 0;
@@ -355,21 +306,21 @@ template <bool HYB, bool STEREO, int CH> WVB_DEV bool decode_word(BitReader &br,
             uint32_t low, high; // WordsUtils.cs:433-475
             {
                 const int m0 = med[0], m1 = med[1], m2 = med[2];
-                const int g0 = addk<1>(m0 >> 4, one), g1 = addk<1>(m1 >> 4, one), g2 = addk<1>(m2 >> 4, one);
+                const int g0 = (m0 >> 4) + 1, g1 = (m1 >> 4) + 1, g2 = (m2 >> 4) + 1;
                 const bool p1 = ones >= 1, p2 = ones >= 2, p3 = ones >= 3;
                 // ones == 0 decrements m0, more increments it; m1 moves only from ones >= 1 (down at 1, up above), m2 from 2
-                med[0] = m0 + ((p1 ? addk<128>(m0, one) : addk<126>(m0, one)) >> 7) * (p1 ? 5 : -2);
-                med[1] = m1 + ((p2 ? addk<64>(m1, one) : addk<62>(m1, one)) >> 6) * (p1 ? (p2 ? 5 : -2) : 0);
-                med[2] = m2 + ((p3 ? addk<32>(m2, one) : addk<30>(m2, one)) >> 5) * (p2 ? (p3 ? 5 : -2) : 0);
-                low = (p1 ? (uint32_t)g0 : 0u) + (p2 ? (uint32_t)g1 : 0u) + (p3 ? (uint32_t)(addk<-2>(ones, one) * g2) : 0u);
-                high = addk<-1>(low + (uint32_t)(p2 ? g2 : p1 ? g1 : g0), one);
+                med[0] = m0 + ((m0 + (p1 ? 128 : 126)) >> 7) * (p1 ? 5 : -2);
+                med[1] = m1 + ((m1 + (p2 ? 64 : 62)) >> 6) * (p1 ? (p2 ? 5 : -2) : 0);
+                med[2] = m2 + ((m2 + (p3 ? 32 : 30)) >> 5) * (p2 ? (p3 ? 5 : -2) : 0);
+                low = (p1 ? (uint32_t)g0 : 0u) + (p2 ? (uint32_t)g1 : 0u) + (p3 ? (uint32_t)((ones - 2) * g2) : 0u);
+                high = low + (uint32_t)(p2 ? g2 : p1 ? g1 : g0) - 1u;
             }
 
             uint32_t mid, sign;
             bool lossless_code = true;
             if constexpr (HYB) lossless_code = w.errlim[CH] == 0;
             const uint32_t range = high - low;
-            const int bitcount = bit_length(range, one);
+            const int bitcount = 32 - wvb_clz(range);
             if (lossless_code && bitcount < 31) {
                 // read_code (WordsUtils.cs:546-570) and the sign bit (494-497) out of one 32-bit look-ahead: at most
                 // bitcount-1 code bits, one extra bit and the sign, 31 bits in all
@@ -842,7 +793,7 @@ template <bool STEREO> WVB_DEV uint32_t next_piece_event(uint32_t t, uint32_t ps
 // for STEREO && !GENFIX.
 template <bool STEREO, bool HYB, bool GENFIX, class SMEM, class DEC = GenericDecorr<STEREO>, bool F16 = false>
 WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc &D, uint8_t *out, int out_format, wvb_block_result *res,
-                              bool valid = true, int one = 1)
+                              bool valid = true)
 {
     const uint8_t *blk = in + D.in_offset;
     const uint32_t flags = D.flags;
@@ -993,12 +944,10 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
     }
 
     BitReader br;
-    br.one = one;
     br.init(blk + D.sub_off[WVB_SUB_WV], D.sub_len[WVB_SUB_WV]);
 
     Fixup fx;
     BitReader wvx;
-    wvx.one = one;
     int crc_x = -1, crc_mvx = 0;
     bool wvx_here = false;
     if (GENFIX) {
