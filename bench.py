@@ -533,7 +533,8 @@ def main():
         results = (N.BlockResult * max(cp.nblocks, 1))()
 
         def step_e2e():
-            c2 = Corpus(slab, corpus["offsets"], corpus["sizes"], out_format=N.OUT_PCM, threads=threads)
+            # (cap_hint: a caller that decodes batch after batch sizes its block table from the previous one and saves the counting walk)
+            c2 = Corpus(slab, corpus["offsets"], corpus["sizes"], out_format=N.OUT_PCM, threads=threads, cap_hint=cp.nblocks)
             dec.decode(slab.ctypes.data, slab.size, c2.descs, c2.nblocks, out_np.ctypes.data, pcm_bytes, N.OUT_PCM, 0, results)
             return c2
 
@@ -570,7 +571,7 @@ def main():
         results_v = (N.BlockResult * max(cp.nblocks, 1))()
 
         def step_verify():
-            c2 = Corpus(slab, corpus["offsets"], corpus["sizes"], out_format=N.OUT_PCM, threads=threads)
+            c2 = Corpus(slab, corpus["offsets"], corpus["sizes"], out_format=N.OUT_PCM, threads=threads, cap_hint=cp.nblocks)
             dec.decode(slab.ctypes.data, slab.size, c2.descs, c2.nblocks, d_out.data_ptr(), pcm_bytes, N.OUT_PCM, N.OUT_DEVICE, results_v)
             lens = np.array([int(c2.infos[i].indexed_samples) * 4 for i in range(c2.nfiles)], dtype=np.uint64)
             return c2, dec.md5_ranges(c2.file_out_offset, lens, pcm_bytes, d_out.data_ptr())

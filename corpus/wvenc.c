@@ -537,6 +537,28 @@ static void ob_le16(obuf *o, unsigned v) { ob_u8(o, v); ob_u8(o, v >> 8); }
 static void ob_le32(obuf *o, u32 v) { ob_le16(o, v); ob_le16(o, v >> 16); }
 
 /* sub-block TLV, MetadataUtils.cs:25-82 */
+static void put_meta(obuf *o, unsigned id, const uint8_t *data, size_t len);
+
+/* WavPack 5 block checksum (ID_BLOCK_CHECKSUM, Defines.cs:83; the reference only notes its presence, MetadataUtils.cs:183).
+ * Definition as published in WavPack 5's libwavpack (block_add_checksum / WavpackVerifySingleBlock): the header gets
+ * HAS_CHECKSUM (0x10000000) and its final ckSize first; then csum = 0xffffffff, csum = csum * 3 + w over every 16-bit
+ * little-endian word of the block up to the checksum sub-block; stored as 4 bytes, or as 2 bytes of csum ^ (csum >> 16).
+ * It is the last sub-block of the block. */
+static void put_block_checksum(obuf *o, size_t hdr_at, int bytes)
+{
+    if (o->overflow) return;
+    u32 flags, cks = (u32)(o->len - hdr_at - 8 + 2 + (size_t)bytes), csum = 0xffffffffu;
+    memcpy(&flags, o->p + hdr_at + 24, 4);
+    flags |= 0x10000000u;
+    memcpy(o->p + hdr_at + 24, &flags, 4);
+    memcpy(o->p + hdr_at + 4, &cks, 4);
+    for (size_t i = hdr_at; i + 1 < o->len; i += 2) csum = csum * 3u + ((u32)o->p[i] | ((u32)o->p[i + 1] << 8));
+    uint8_t tmp[4];
+    if (bytes == 2) csum ^= csum >> 16;
+    tmp[0] = (uint8_t)csum; tmp[1] = (uint8_t)(csum >> 8); tmp[2] = (uint8_t)(csum >> 16); tmp[3] = (uint8_t)(csum >> 24);
+    put_meta(o, 0x2f, tmp, (size_t)bytes);
+}
+
 static void put_meta(obuf *o, unsigned id, const uint8_t *data, size_t len)
 {
     size_t words = (len + 1) >> 1;
@@ -958,7 +980,7 @@ static void encode_pcm_block(encoder *E, stream_state *S, const i32 *srcL, const
         put_meta(o, newfmt ? 0x2c : 0x0c, blob, plen);
         free(blob);
     }
-    if (cfg->extras & WVENC_X_BLOCK_CHECKSUM) { tmp[0] = 0x12; tmp[1] = 0x34; put_meta(o, 0x2f, tmp, 2); }
+    if (cfg->extras & WVENC_X_BLOCK_CHECKSUM) put_block_checksum(o, hdr_at, 4);
     if (!o->overflow) {
         u32 cks = (u32)(o->len - hdr_at - 8);
         memcpy(o->p + hdr_at + 4, &cks, 4);
@@ -1143,7 +1165,7 @@ static void encode_dsd_block(encoder *E, const i32 *src, int nch, i64 n, i64 blo
     if (!len) o->overflow = 1;
     else put_meta(o, 0x0e, pl, len);
     free(pl);
-    if (cfg->extras & WVENC_X_BLOCK_CHECKSUM) { tmp[0] = 0x12; tmp[1] = 0x34; put_meta(o, 0x2f, tmp, 2); }
+    if (cfg->extras & WVENC_X_BLOCK_CHECKSUM) put_block_checksum(o, hdr_at, 2);
     if (!o->overflow) {
         u32 cks = (u32)(o->len - hdr_at - 8);
         memcpy(o->p + hdr_at + 4, &cks, 4);

@@ -44,7 +44,7 @@ namespace WavPack
             public ushort version;
             public byte out_channels, out_stride, out_ch_offset, out_bps;
             public ushort smem_words;
-            public uint chunk_first, chunk_samples, file_id, gap_before, terms_sig, skip_samples, skip_chunk, avg_block_size, reserved;
+            public uint chunk_first, chunk_samples, file_id, gap_before, terms_sig, skip_samples, skip_chunk, avg_block_size, checksum_off;
         }
 
         [StructLayout(LayoutKind.Sequential)]

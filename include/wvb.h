@@ -77,6 +77,7 @@ enum {
 #define WVB_BF_MUTE_ALL 16u      /* reference reaches this block without unpack_init (after a gap): output zeros, count a CRC error */
 #define WVB_BF_STALE_STATE 32u   /* block depends on decoder state left by an earlier block; result flagged inexact */
 #define WVB_BF_DSD_PADDED 64u    /* DSD payload array includes the pad byte (data.Length quirk C-10) */
+#define WVB_BF_BLOCK_CHECKSUM 128u /* the block ends with a well-formed ID_BLOCK_CHECKSUM sub-block at checksum_off */
 
 /*
  * One decodable block, as produced by wvb_index (file-relative offsets) and consumed
@@ -113,7 +114,7 @@ typedef struct wvb_block_desc {
     uint32_t skip_chunk;    /* ... this many samples (SAMPLE_BUFFER_SIZE / channels, WavPackUtils.cs:573-578); both 0 otherwise */
     uint32_t avg_block_size; /* wphdr.average_block_size after this block's header was read (WavPackUtils.cs:647-650): the
                                 reference's seek() extrapolates file positions from it */
-    uint32_t reserved;
+    uint32_t checksum_off;  /* WVB_BF_BLOCK_CHECKSUM: offset of the ID_BLOCK_CHECKSUM sub-block (its id byte) from in_offset */
 } wvb_block_desc;
 
 /* per-block result.  Replaces wps.crc / mute_error / check_crc_error (UnpackUtils.cs:1414-1421). 16 bytes */
@@ -122,6 +123,8 @@ typedef struct wvb_block_desc {
 #define WVB_RF_CRCX_ERROR 4u    /* extended (WVX) crc mismatch */
 #define WVB_RF_INEXACT 8u       /* corrupt-stream corner the device path does not reproduce bit-exactly */
 #define WVB_RF_BAD_BLOCK 16u    /* device-side metadata validation failed (DSD tables) */
+#define WVB_RF_BLOCK_CHECKSUM 32u /* the WavPack 5 block checksum does not match the block's bytes.  An extension: the reference
+                                     only notes the sub-block (MetadataUtils.cs:183), so output and crc_errors are unaffected */
 typedef struct wvb_block_result {
     int32_t crc;           /* crc accumulated by the decoder */
     uint32_t rflags;       /* WVB_RF_* */
@@ -219,7 +222,10 @@ int wvb_index_seek(const uint8_t *file, size_t len, uint32_t open_flags, const w
 /* Index many files with `threads` host threads (<=0: all cores).  File i occupies
  * slab[offsets[i] .. offsets[i]+sizes[i]); its descriptors are written to
  * blocks[first[i] .. first[i]+count[i]) (first/count are outputs) already rebased
- * for a file-major output slab in out_format.  out_bytes receives the output slab size. */
+ * for a file-major output slab in out_format.  out_bytes receives the output slab size.
+ * blocks == NULL (cap 0) only counts.  With a table, the files are walked once; if cap turns out too small the call
+ * returns WVB_E_CAPACITY with *nblocks set to the size needed (callers that decode similar batches repeatedly pass the
+ * previous count as cap and skip the counting call). */
 int wvb_index_many(const uint8_t *slab, const uint64_t *offsets, const uint64_t *sizes, size_t nfiles, uint32_t open_flags,
                    uint32_t chunk_samples, int out_format, int threads, wvb_file_info *infos, wvb_block_desc *blocks, size_t cap,
                    uint64_t *first, uint64_t *count, uint64_t *file_out_offset, size_t *nblocks, uint64_t *out_bytes);
@@ -275,6 +281,14 @@ int wvb_batch_md5(wvb_batch *b, const void *device_out, size_t out_bytes, const 
 /* The MD5 a .wv file stores for its source audio (ID_MD5_CHECKSUM, Defines.cs:77), searched in every block's
  * metadata.  Returns 1 and fills md5 if present, 0 if not. */
 int wvb_stored_md5(const uint8_t *file, size_t len, uint8_t md5[16]);
+
+/* The WavPack 5 block checksum of one block (ID_BLOCK_CHECKSUM, Defines.cs:83), on the host: 1 = present and matching,
+ * 0 = present and wrong, -1 = the block has none (or is malformed).  Definition (WavPack 5 libwavpack,
+ * WavpackVerifySingleBlock): csum = 0xffffffff; csum = csum * 3 + w over the 16-bit little-endian words of the block from
+ * its 'wvpk' up to the checksum sub-block; stored as 4 bytes, or as the 2 bytes of csum ^ (csum >> 16).  wvb_batch_decode
+ * checks the same thing on the device for every block that has one (a warp per block, after the decode kernels) and reports
+ * WVB_RF_BLOCK_CHECKSUM. */
+int wvb_block_checksum_ok(const uint8_t *block, size_t len);
 
 /* pinned host memory helpers for hosts without their own allocator (C# shim) */
 void *wvb_host_alloc(size_t bytes);

@@ -18,8 +18,8 @@ OPEN_2CH_MAX = 0x8
 OPEN_ALL_CHANNELS = 0x10000
 OUT_INT32, OUT_PCM, OUT_DSD_RAW = 0, 1, 2
 IN_DEVICE, OUT_DEVICE, RESULTS_DEVICE, NO_SYNC = 1, 2, 4, 8
-RF_CRC_ERROR, RF_MUTED, RF_CRCX_ERROR, RF_INEXACT, RF_BAD_BLOCK = 1, 2, 4, 8, 16
-BF_WVX_NEW, BF_HAS_INT32_INFO, BF_HAS_FLOAT_INFO, BF_WVX_PRESENT, BF_MUTE_ALL, BF_STALE_STATE, BF_DSD_PADDED = 1, 2, 4, 8, 16, 32, 64
+RF_CRC_ERROR, RF_MUTED, RF_CRCX_ERROR, RF_INEXACT, RF_BAD_BLOCK, RF_BLOCK_CHECKSUM = 1, 2, 4, 8, 16, 32
+BF_WVX_NEW, BF_HAS_INT32_INFO, BF_HAS_FLOAT_INFO, BF_WVX_PRESENT, BF_MUTE_ALL, BF_STALE_STATE, BF_DSD_PADDED, BF_BLOCK_CHECKSUM = 1, 2, 4, 8, 16, 32, 64, 128
 
 
 class BlockDesc(C.Structure):
@@ -31,7 +31,7 @@ class BlockDesc(C.Structure):
         ("out_channels", C.c_uint8), ("out_stride", C.c_uint8), ("out_ch_offset", C.c_uint8), ("out_bps", C.c_uint8),
         ("smem_words", C.c_uint16), ("chunk_first", C.c_uint32), ("chunk_samples", C.c_uint32), ("file_id", C.c_uint32),
         ("gap_before", C.c_uint32), ("terms_sig", C.c_uint32), ("skip_samples", C.c_uint32), ("skip_chunk", C.c_uint32),
-        ("avg_block_size", C.c_uint32), ("reserved", C.c_uint32),
+        ("avg_block_size", C.c_uint32), ("checksum_off", C.c_uint32),
     ]
 
 
@@ -67,7 +67,7 @@ def desc_table(descs, n):
                    ("block_index", "<i8"), ("sub_off", "<u4", (8,)), ("sub_len", "<u4", (8,)), ("int32_info", "u1", (4,)), ("float_info", "u1", (4,)),
                    ("bflags", "<u4"), ("version", "<u2"), ("out_channels", "u1"), ("out_stride", "u1"), ("out_ch_offset", "u1"), ("out_bps", "u1"),
                    ("smem_words", "<u2"), ("chunk_first", "<u4"), ("chunk_samples", "<u4"), ("file_id", "<u4"), ("gap_before", "<u4"),
-                   ("terms_sig", "<u4"), ("skip_samples", "<u4"), ("skip_chunk", "<u4"), ("avg_block_size", "<u4"), ("reserved", "<u4")])
+                   ("terms_sig", "<u4"), ("skip_samples", "<u4"), ("skip_chunk", "<u4"), ("avg_block_size", "<u4"), ("checksum_off", "<u4")])
     assert dt.itemsize == C.sizeof(BlockDesc)
     return np.frombuffer(descs, dtype=dt, count=n)
 
@@ -82,7 +82,7 @@ assert C.sizeof(BlockResult) == 16
 EXPORTS = [
     "wvb_abi_version", "wvb_abi_layout", "wvb_last_error", "wvb_device_count", "wvb_index", "wvb_index_seek", "wvb_index_many", "wvb_rebase", "wvb_frame_bytes",
     "wvb_batch_create", "wvb_batch_destroy", "wvb_batch_prepare", "wvb_batch_decode", "wvb_batch_wait", "wvb_batch_timing", "wvb_batch_stream",
-    "wvb_host_alloc", "wvb_host_free", "wvb_batch_md5", "wvb_stored_md5",
+    "wvb_host_alloc", "wvb_host_free", "wvb_batch_md5", "wvb_stored_md5", "wvb_block_checksum_ok",
 ]
 
 
@@ -106,6 +106,8 @@ def declare_index_api(lib):
     lib.wvb_stored_md5.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
     lib.wvb_stored_md5.restype = C.c_int
     lib.wvb_abi_layout.restype = C.c_char_p
+    lib.wvb_block_checksum_ok.argtypes = [C.c_void_p, C.c_size_t]
+    lib.wvb_block_checksum_ok.restype = C.c_int
     return lib
 
 

@@ -26,7 +26,7 @@ class Corpus:
     slab: uint8 numpy array (ideally pinned), offsets/sizes: per-file byte ranges.
     """
 
-    def __init__(self, slab, offsets, sizes, open_flags=0, chunk_samples=4096, out_format=N.OUT_PCM, threads=0):
+    def __init__(self, slab, offsets, sizes, open_flags=0, chunk_samples=4096, out_format=N.OUT_PCM, threads=0, cap_hint=0):
         lib = N.load()
         self.lib = lib
         self.slab = slab
@@ -43,16 +43,23 @@ class Corpus:
         out_bytes = C.c_uint64()
         args = (slab.ctypes.data, self.offsets.ctypes.data, self.sizes.ctypes.data, self.nfiles, open_flags, chunk_samples,
                 out_format, threads, self.infos)
-        rc = lib.wvb_index_many(*args, None, 0, self.first.ctypes.data, self.count.ctypes.data, self.file_out_offset.ctypes.data,
-                                C.byref(nblocks), C.byref(out_bytes))
-        _check(lib, rc, "wvb_index_many(count)")
-        self.nblocks = nblocks.value
-        # the table is filled by the library: backing it with uninitialised numpy memory skips ctypes' zero fill (10 ms at 200 000 blocks)
-        self._descs_mem = np.empty(max(self.nblocks, 1) * C.sizeof(N.BlockDesc), dtype=np.uint8)
-        self.descs = (N.BlockDesc * max(self.nblocks, 1)).from_buffer(self._descs_mem)
-        rc = lib.wvb_index_many(*args, self.descs, self.nblocks, self.first.ctypes.data, self.count.ctypes.data,
-                                self.file_out_offset.ctypes.data, C.byref(nblocks), C.byref(out_bytes))
+        tail = (self.first.ctypes.data, self.count.ctypes.data, self.file_out_offset.ctypes.data, C.byref(nblocks), C.byref(out_bytes))
+
+        def table(cap):
+            # the table is filled by the library: backing it with uninitialised numpy memory skips ctypes' zero fill (10 ms at 200 000 blocks)
+            self._descs_mem = np.empty(max(cap, 1) * C.sizeof(N.BlockDesc), dtype=np.uint8)
+            self.descs = (N.BlockDesc * max(cap, 1)).from_buffer(self._descs_mem)
+            return lib.wvb_index_many(*args, self.descs, cap, *tail)
+
+        # cap_hint (e.g. the block count of the previous, similar batch) saves the counting walk; a hint that turns out too
+        # small costs one more walk with the exact size
+        rc = table(int(cap_hint)) if cap_hint else N.E_CAPACITY
+        if rc == N.E_CAPACITY:
+            if not cap_hint:
+                _check(lib, lib.wvb_index_many(*args, None, 0, *tail), "wvb_index_many(count)")
+            rc = table(nblocks.value)
         _check(lib, rc, "wvb_index_many")
+        self.nblocks = nblocks.value
         self.out_bytes = int(out_bytes.value)
 
     @classmethod

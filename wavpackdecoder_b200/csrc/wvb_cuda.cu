@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -16,6 +17,7 @@
 #include <string>
 #include <vector>
 
+#include "wvb_checksum.cuh"
 #include "wvb_dsd.cuh"
 #include "wvb_md5.cuh"
 #include "wvb_pcm.cuh"
@@ -92,8 +94,16 @@ struct wvb_batch {
     std::vector<Launch> plan;
     size_t prepared_n = 0; bool prepared = false; int prepared_fmt = -1;
     uint64_t prepared_in_extent = 0, prepared_out_extent = 0; // slab sizes the prepared table needs
-    std::vector<wvb_block_result> host_results;
+    // pinned staging of the small per-call arrays: copies from / into pageable memory are staged by the driver and block the
+    // host thread on the stream they are queued on
+    uint32_t *h_order = nullptr; size_t h_order_cap = 0;
+    wvb_block_result *h_results = nullptr; size_t h_results_cap = 0;
     wvb_block_result *pending_results = nullptr; size_t pending_n = 0; bool pending_copy = false;
+    // WVB_TRACE=1: per-segment timeline of the pipelined host-buffer decode, printed by wvb_batch_wait
+    struct TraceSeg { cudaEvent_t up, dec, down; size_t blocks; uint64_t in_bytes, out_bytes; double host_ms; };
+    std::vector<TraceSeg> trace;
+    cudaEvent_t trace_t0 = nullptr;
+    double trace_host_total_ms = 0;
     int launches = 0;
     cudaStream_t s_in = nullptr, s_out = nullptr; // copy streams of the pipelined host-buffer path
     std::vector<cudaEvent_t> seg_ev;
@@ -105,6 +115,17 @@ struct wvb_batch {
 };
 
 namespace {
+
+template <class T> int ensure_pinned(T *&p, size_t &cap, size_t need)
+{
+    if (need <= cap) return WVB_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    const size_t want = need + need / 8 + 256;
+    CUDA_TRY(cudaHostAlloc((void **)&p, want * sizeof(T), cudaHostAllocDefault));
+    cap = want;
+    return WVB_OK;
+}
 
 template <class T> int ensure(T *&p, size_t &cap, size_t need)
 {
@@ -166,8 +187,10 @@ void make_plan(const wvb_block_desc *descs, size_t n, int fmt, std::vector<uint3
     order.resize(n);
     std::iota(order.begin(), order.end(), 0u);
     std::vector<uint64_t> key(n);
+    bool any_checksum = false;
     for (size_t i = 0; i < n; i++) {
         const wvb_block_desc &d = descs[i];
+        any_checksum |= (d.bflags & WVB_BF_BLOCK_CHECKSUM) != 0;
         int v = wvb::variant_of(d);
         // 16-bit interleaved stereo PCM gets its own launches: one aligned word store per frame, no byte-packing state
         if ((v & ~(wvb::V_FIXED | wvb::V_FIXED_B | wvb::V_FIXED_C)) == wvb::V_STEREO && wvb::block_is_fast16(d, fmt == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : fmt)) v |= wvb::V_F16;
@@ -198,6 +221,7 @@ void make_plan(const wvb_block_desc *descs, size_t n, int fmt, std::vector<uint3
         launches.push_back(L);
         i = j;
     }
+    if (any_checksum && n) launches.push_back(Launch{wvb::V_CHECKSUM, 0, 0u, (uint32_t)n}); // after the decode launches: it ORs into their results
 }
 
 } // namespace
@@ -242,6 +266,10 @@ void wvb_batch_destroy(wvb_batch *b)
     cudaFree(b->d_md5_ranges); cudaFree(b->d_md5_out);
     cudaFree(b->d_in); cudaFree(b->d_out); cudaFree(b->d_descs); cudaFree(b->d_order); cudaFree(b->d_results);
     cudaFree(b->d_scratch); cudaFree(b->d_scratch_meta);
+    if (b->h_order) cudaFreeHost(b->h_order);
+    if (b->h_results) cudaFreeHost(b->h_results);
+    for (auto &t : b->trace) { cudaEventDestroy(t.up); cudaEventDestroy(t.dec); cudaEventDestroy(t.down); }
+    if (b->trace_t0) cudaEventDestroy(b->trace_t0);
     for (auto &e : b->ev) if (e) cudaEventDestroy(e);
     for (auto &e : b->seg_ev) if (e) cudaEventDestroy(e);
     for (auto &st : b->seg_streams) if (st) cudaStreamDestroy(st);
@@ -259,8 +287,22 @@ int wvb_batch_wait(wvb_batch *b)
     CUDA_TRY(cudaSetDevice(b->device));
     CUDA_TRY(cudaStreamSynchronize(b->stream));
     if (b->pending_copy && b->pending_results) {
-        memcpy(b->pending_results, b->host_results.data(), b->pending_n * sizeof(wvb_block_result));
+        memcpy(b->pending_results, b->h_results, b->pending_n * sizeof(wvb_block_result));
         b->pending_copy = false;
+    }
+    if (!b->trace.empty() && b->trace_t0) {
+        fprintf(stderr, "[wvb trace] pipelined decode, %zu segments, host queueing %.2f ms; times in ms since the call began (device clock)\n",
+                b->trace.size(), b->trace_host_total_ms);
+        for (size_t k = 0; k < b->trace.size(); k++) {
+            float up = 0, dec = 0, down = 0;
+            cudaEventElapsedTime(&up, b->trace_t0, b->trace[k].up);
+            cudaEventElapsedTime(&dec, b->trace_t0, b->trace[k].dec);
+            cudaEventElapsedTime(&down, b->trace_t0, b->trace[k].down);
+            fprintf(stderr, "[wvb trace] seg %2zu: %7zu blocks  in %7.1f MB  out %7.1f MB  queued@%7.2f  uploaded@%7.2f  decoded@%7.2f  downloaded@%7.2f\n", k,
+                    b->trace[k].blocks, b->trace[k].in_bytes / 1e6, b->trace[k].out_bytes / 1e6, b->trace[k].host_ms, up, dec, down);
+        }
+        for (auto &t : b->trace) { cudaEventDestroy(t.up); cudaEventDestroy(t.dec); cudaEventDestroy(t.down); }
+        b->trace.clear();
     }
     return WVB_OK;
 }
@@ -365,6 +407,13 @@ static int launch_plan(wvb_batch *b, const std::vector<Launch> &plan, const uint
 {
     int rc;
     for (const Launch &L : plan) {
+        if (L.variant == wvb::V_CHECKSUM) {
+            constexpr unsigned per = wvb::CHECKSUM_THREADS / 32;
+            wvb::k_block_checksum<<<(L.count + per - 1) / per, wvb::CHECKSUM_THREADS, 0, s>>>(din, b->d_descs, b->d_order + L.first, L.count, dres);
+            CUDA_TRY(cudaGetLastError());
+            b->launches++;
+            continue;
+        }
         if (L.variant == wvb::V_DSD) {
             // fast mode: scratch slots are indexed by position in the order array, so concurrent launches never share one
             if (L.cls >= 16 && ((size_t)L.first + L.count) * wvb::DSD_FAST_TABLE_STRIDE > b->d_scratch_cap)
@@ -486,7 +535,17 @@ static int decode_pipelined_queue(wvb_batch *b, const uint8_t *in, size_t in_byt
     if ((rc = ensure(b->d_results, b->d_results_cap, nblocks + 1)) != WVB_OK) return rc;
     if ((rc = ensure(b->d_descs, b->d_descs_cap, nblocks + 1)) != WVB_OK) return rc;
     if ((rc = ensure(b->d_order, b->d_order_cap, nblocks + 1)) != WVB_OK) return rc;
+    if ((rc = ensure_pinned(b->h_order, b->h_order_cap, nblocks + 1)) != WVB_OK) return rc;
     cudaStream_t s = b->stream;
+    static const bool tracing = getenv("WVB_TRACE") && atoi(getenv("WVB_TRACE"));
+    const auto host_t0 = std::chrono::steady_clock::now();
+    auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
+    for (auto &t : b->trace) { cudaEventDestroy(t.up); cudaEventDestroy(t.dec); cudaEventDestroy(t.down); }
+    b->trace.clear();
+    if (tracing) {
+        if (!b->trace_t0) CUDA_TRY(cudaEventCreate(&b->trace_t0));
+        CUDA_TRY(cudaEventRecord(b->trace_t0, s));
+    }
 
     // Order of the host work matters here.  The table goes up first; then every segment is planned (a sort), its slice of
     // the launch order and its slab bytes are queued on the upload stream, and its kernels are launched -- so the first
@@ -521,23 +580,36 @@ static int decode_pipelined_queue(wvb_batch *b, const uint8_t *in, size_t in_byt
         const Seg &g = segs[k];
         cudaStream_t ks = b->seg_streams[k];
         if (!needs_scratch) plan_segment(k);
-        CUDA_TRY(cudaMemcpyAsync(b->d_order + g.first, b->order.data() + g.first, g.count * sizeof(uint32_t), cudaMemcpyHostToDevice, b->s_in));
+        memcpy(b->h_order + g.first, b->order.data() + g.first, g.count * sizeof(uint32_t));
+        CUDA_TRY(cudaMemcpyAsync(b->d_order + g.first, b->h_order + g.first, g.count * sizeof(uint32_t), cudaMemcpyHostToDevice, b->s_in));
         CUDA_TRY(cudaMemcpyAsync(b->d_in + g.in_lo, in + g.in_lo, g.in_hi - g.in_lo, cudaMemcpyHostToDevice, b->s_in));
         CUDA_TRY(cudaEventRecord(b->seg_ev[2 * k], b->s_in));
+        wvb_batch::TraceSeg tr{nullptr, nullptr, nullptr, g.count, g.in_hi - g.in_lo, g.out_hi - g.out_lo, 0};
+        if (tracing) {
+            CUDA_TRY(cudaEventCreate(&tr.up)); CUDA_TRY(cudaEventCreate(&tr.dec)); CUDA_TRY(cudaEventCreate(&tr.down));
+            CUDA_TRY(cudaEventRecord(tr.up, b->s_in));
+        }
         CUDA_TRY(cudaStreamWaitEvent(ks, b->seg_ev[2 * k], 0)); // table (s_in waited for it), this segment's order slice and input
         if ((rc = launch_plan(b, plans[k], b->d_in, dout, fmt, b->d_results, ks)) != WVB_OK) return rc;
         CUDA_TRY(cudaEventRecord(b->seg_ev[2 * k + 1], ks));
         CUDA_TRY(cudaStreamWaitEvent(b->s_out, b->seg_ev[2 * k + 1], 0));
         CUDA_TRY(cudaStreamWaitEvent(s, b->seg_ev[2 * k + 1], 0));
         if (!out_device) CUDA_TRY(cudaMemcpyAsync(out + g.out_lo, dout + g.out_lo, g.out_hi - g.out_lo, cudaMemcpyDeviceToHost, b->s_out));
+        if (tracing) {
+            CUDA_TRY(cudaEventRecord(tr.dec, ks));
+            CUDA_TRY(cudaEventRecord(tr.down, b->s_out));
+            tr.host_ms = host_ms();
+            b->trace.push_back(tr);
+        }
     }
+    b->trace_host_total_ms = host_ms();
     CUDA_TRY(cudaEventRecord(b->ev[2], s));
     CUDA_TRY(cudaEventRecord(b->seg_ev[2 * segs.size() + 1], b->s_out));
     CUDA_TRY(cudaStreamWaitEvent(s, b->seg_ev[2 * segs.size() + 1], 0));
     b->pending_copy = false;
     if (results) {
-        b->host_results.resize(nblocks);
-        CUDA_TRY(cudaMemcpyAsync(b->host_results.data(), b->d_results, nblocks * sizeof(wvb_block_result), cudaMemcpyDeviceToHost, s));
+        if ((rc = ensure_pinned(b->h_results, b->h_results_cap, nblocks + 1)) != WVB_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(b->h_results, b->d_results, nblocks * sizeof(wvb_block_result), cudaMemcpyDeviceToHost, s));
         b->pending_results = results;
         b->pending_n = nblocks;
         b->pending_copy = true;
@@ -628,8 +700,8 @@ int wvb_batch_decode(wvb_batch *b, const uint8_t *in, size_t in_bytes, const wvb
     if (!(mem_flags & WVB_OUT_DEVICE)) CUDA_TRY(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, s));
     b->pending_copy = false;
     if (results && !(mem_flags & WVB_RESULTS_DEVICE)) {
-        b->host_results.resize(nblocks);
-        if (nblocks) CUDA_TRY(cudaMemcpyAsync(b->host_results.data(), dres, nblocks * sizeof(wvb_block_result), cudaMemcpyDeviceToHost, s));
+        if ((rc = ensure_pinned(b->h_results, b->h_results_cap, nblocks + 1)) != WVB_OK) return rc;
+        if (nblocks) CUDA_TRY(cudaMemcpyAsync(b->h_results, dres, nblocks * sizeof(wvb_block_result), cudaMemcpyDeviceToHost, s));
         b->pending_results = results;
         b->pending_n = nblocks;
         b->pending_copy = true;

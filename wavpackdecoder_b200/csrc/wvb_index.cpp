@@ -376,7 +376,13 @@ bool unpack_init(Ctx &c)
             I.file_extension[n] = 0;
             break;
         }
-        case 0x2f: I.five = 1; break; // ID_BLOCK_CHECKSUM
+        case 0x2f: // ID_BLOCK_CHECKSUM: the reference notes it (MetadataUtils.cs:183); the batch decoder verifies it on the device
+            I.five = 1;
+            if ((byte_length == 2 || byte_length == 4) && bytes_to_read == byte_length && !(rel & 1)) {
+                B.bflags |= WVB_BF_BLOCK_CHECKSUM;
+                B.checksum_off = rel - 2;
+            }
+            break;
         default:
             if (!(id & 0x20)) return fail_id(id);
             break;
@@ -646,7 +652,7 @@ const char *wvb_abi_layout(void)
         F(wvb_block_desc, out_channels); F(wvb_block_desc, out_stride); F(wvb_block_desc, out_ch_offset); F(wvb_block_desc, out_bps);
         F(wvb_block_desc, smem_words); F(wvb_block_desc, chunk_first); F(wvb_block_desc, chunk_samples); F(wvb_block_desc, file_id);
         F(wvb_block_desc, gap_before); F(wvb_block_desc, terms_sig); F(wvb_block_desc, skip_samples); F(wvb_block_desc, skip_chunk);
-        F(wvb_block_desc, avg_block_size); F(wvb_block_desc, reserved);
+        F(wvb_block_desc, avg_block_size); F(wvb_block_desc, checksum_off);
         S(wvb_block_result);
         F(wvb_block_result, crc); F(wvb_block_result, rflags); F(wvb_block_result, mute_from); F(wvb_block_result, crc_x);
         S(wvb_file_info);
@@ -842,6 +848,35 @@ int wvb_stored_md5(const uint8_t *file, size_t len, uint8_t md5[16])
     return 0;
 }
 
+int wvb_block_checksum_ok(const uint8_t *block, size_t len)
+{
+    if (!block || len < 32 || memcmp(block, "wvpk", 4) != 0) return -1;
+    const size_t end = std::min<size_t>(len, (size_t)le32(block + 4) + 8);
+    size_t at = 32;
+    while (at + 2 <= end) {
+        const uint8_t id = block[at];
+        size_t words = block[at + 1], hdr = 2;
+        if (id & 0x80) {
+            if (at + 4 > end) return -1;
+            words |= ((size_t)block[at + 2] << 8) | ((size_t)block[at + 3] << 16);
+            hdr = 4;
+        }
+        if (at + hdr + 2 * words > end) return -1;
+        if ((id & 0x3f) == 0x2f) {
+            const size_t n = 2 * words;
+            if ((id & 0x40) || hdr != 2 || (n != 2 && n != 4) || (at & 1)) return -1;
+            uint32_t csum = 0xffffffffu;
+            for (size_t i = 0; i < at; i += 2) csum = csum * 3u + ((uint32_t)block[i] | ((uint32_t)block[i + 1] << 8));
+            const uint8_t *st = block + at + 2;
+            if (n == 4) return le32(st) == csum;
+            csum ^= csum >> 16;
+            return ((uint32_t)st[0] | ((uint32_t)st[1] << 8)) == (csum & 0xffffu);
+        }
+        at += hdr + 2 * words;
+    }
+    return -1;
+}
+
 uint32_t wvb_frame_bytes(const wvb_block_desc *b, int out_format)
 {
     uint32_t unit = out_format == WVB_OUT_INT32 ? 4u : b->out_bps;
@@ -865,24 +900,45 @@ int wvb_index_many(const uint8_t *slab, const uint64_t *offsets, const uint64_t 
     if (!slab || !offsets || !sizes || !infos || !first || !count) return WVB_E_ARG;
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
     threads = (int)std::min<size_t>((size_t)threads, std::max<size_t>(nfiles, 1));
-    // pass 1: count blocks per file (the walk is cheap; doing it twice keeps the output table dense and ordered)
+    // One walk over the files.  With a table to fill, every worker collects the descriptors of the files it takes in a
+    // buffer of its own (files are handed out dynamically, so the final position of a file's descriptors is only known
+    // once every file before it has been counted); a second, copy-only step moves them into the dense, file-ordered table.
+    struct Piece { int worker; size_t start; };
+    std::vector<Piece> piece(blocks ? nfiles : 0);
+    std::vector<std::vector<wvb_block_desc>> local(blocks ? (size_t)threads : 0);
     std::atomic<size_t> next{0};
-    auto worker1 = [&]() {
+    auto walk = [&](int w) {
+        std::vector<wvb_block_desc> *mine = blocks ? &local[(size_t)w] : nullptr;
+        if (mine) mine->reserve(cap / (size_t)threads + 64);
         for (;;) {
-            size_t i = next.fetch_add(1);
+            const size_t i = next.fetch_add(1);
             if (i >= nfiles) break;
             size_t n = 0;
-            wvb_index(slab + offsets[i], (size_t)sizes[i], open_flags, chunk_samples, &infos[i], nullptr, 0, &n);
+            if (!mine) {
+                wvb_index(slab + offsets[i], (size_t)sizes[i], open_flags, chunk_samples, &infos[i], nullptr, 0, &n);
+            } else {
+                // grow-and-retry: the file's block count is not known before the walk (rarely more than one retry per worker)
+                const size_t start = mine->size();
+                size_t room = std::max<size_t>(mine->capacity() - start, 64);
+                for (;;) {
+                    mine->resize(start + room);
+                    const int rc = wvb_index(slab + offsets[i], (size_t)sizes[i], open_flags, chunk_samples, &infos[i], mine->data() + start, room, &n);
+                    if (rc != WVB_E_CAPACITY) break;
+                    room = n;
+                }
+                mine->resize(start + n);
+                piece[i] = Piece{w, start};
+            }
             count[i] = n;
         }
     };
     {
         std::vector<std::thread> th;
-        for (int t = 0; t < threads; t++) th.emplace_back(worker1);
+        for (int t = 0; t < threads; t++) th.emplace_back(walk, t);
         for (auto &t : th) t.join();
     }
     uint64_t total = 0, obytes = 0;
-    std::vector<uint64_t> own_offsets; // the caller may not want the per-file offsets; pass 2 needs them either way
+    std::vector<uint64_t> own_offsets; // the caller may not want the per-file offsets; the rebase needs them either way
     if (!file_out_offset) {
         own_offsets.resize(nfiles);
         file_out_offset = own_offsets.data();
@@ -902,19 +958,21 @@ int wvb_index_many(const uint8_t *slab, const uint64_t *offsets, const uint64_t 
     if (!blocks) return WVB_OK;
     if (total > cap) return WVB_E_CAPACITY;
     next = 0;
-    auto worker2 = [&]() {
+    auto gather = [&]() {
         for (;;) {
-            size_t i = next.fetch_add(1);
-            if (i >= nfiles) break;
-            size_t n = 0;
-            wvb_file_info tmp;
-            wvb_index(slab + offsets[i], (size_t)sizes[i], open_flags, chunk_samples, &tmp, blocks + first[i], (size_t)count[i], &n);
-            wvb_rebase(blocks + first[i], n, offsets[i], file_out_offset[i], out_format, (uint32_t)i);
+            const size_t i0 = next.fetch_add(64);
+            if (i0 >= nfiles) break;
+            for (size_t i = i0; i < std::min(nfiles, i0 + 64); i++) {
+                const size_t n = (size_t)count[i];
+                if (!n) continue;
+                memcpy(blocks + first[i], local[(size_t)piece[i].worker].data() + piece[i].start, n * sizeof(wvb_block_desc));
+                wvb_rebase(blocks + first[i], n, offsets[i], file_out_offset[i], out_format, (uint32_t)i);
+            }
         }
     };
     {
         std::vector<std::thread> th;
-        for (int t = 0; t < threads; t++) th.emplace_back(worker2);
+        for (int t = 0; t < threads; t++) th.emplace_back(gather);
         for (auto &t : th) t.join();
     }
     return WVB_OK;

@@ -7,7 +7,8 @@
 namespace wvb {
 
 // kernel variants of the PCM path
-enum { V_MONO = 0, V_STEREO = 1, V_GENFIX = 2, V_HYBRID = 4, V_DSD = 8, V_FIXED = 16, V_F16 = 32, V_FIXED_B = 64, V_FIXED_C = 128, V_COUNT = 256 };
+enum { V_MONO = 0, V_STEREO = 1, V_GENFIX = 2, V_HYBRID = 4, V_DSD = 8, V_FIXED = 16, V_F16 = 32, V_FIXED_B = 64, V_FIXED_C = 128, V_COUNT = 256,
+       V_CHECKSUM = 200 /* not a decode variant: the block-checksum pass over a plan's blocks, queued after its decode launches */ };
 
 // FNV-1a over the term list in DECODER order, as wvb_index computes wvb_block_desc.terms_sig
 constexpr uint32_t terms_hash(const int *t, int n)
