@@ -14,6 +14,12 @@ PCM_CASES = [
     ("terms_all_pos", 0, 4096, dict(terms=[1, 2, 3, 4, 5, 6, 7, 8, 17, 18])),
     ("terms_neg", 0, 4096, dict(terms=[-1, -2, -3, 18, -1, 2])),
     ("terms16", 0, 4096, dict(terms=T16, deltas=[2] * 16)),
+    # state above 128 words per thread: the software-pipelined pass loop and the one-warp CTAs (every term class in it)
+    ("terms16_all_classes", 0, 4096, dict(terms=[1, 2, 3, 4, 5, 6, 7, 8, 17, 18, -1, -2, -3, 8, 7, 6], deltas=[1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3, 4, 5, 6, 7, 2])),
+    ("terms16_mono", 0, 4096, dict(channels=1, terms=[17, 18, 1, 8, 5, 7, 6, 8, 8, 7, 6, 5, 8, 8, 8, 8], deltas=[2] * 16)),
+    ("terms15_odd_count_24bit", 0, 1000, dict(bits=24, terms=[18, 8, 7, 6, 5, 8, 7, 6, -1, 8, 17, 8, -3, 7, 8], deltas=[3] * 15, seconds=0.5)),
+    ("terms16_hybrid", 0, 4096, dict(kind=KIND_HYBRID, terms=T16, deltas=[2] * 16, seconds=0.5)),
+    ("terms16_int32_wvx", 0, 4096, dict(bits=32, int32_sent_bits=8, terms=T16, deltas=[2] * 16, seconds=0.5)),
     ("terms0", 0, 4096, dict(terms=[])),
     ("delta7", 0, 4096, dict(terms=[18, 3, -3], deltas=[7, 0, 5])),
     ("mono_terms", 0, 4096, dict(channels=1, terms=[17, 18, 1, 8, 5])),

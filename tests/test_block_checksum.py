@@ -148,6 +148,7 @@ def test_device_checksum_at_every_slab_alignment():
     base = bytes(make_file(extras=X_CONFIG | X_BLOCK_CHECKSUM, seconds=0.4, block_samples=3000)[2])
     small = bytes(make_file(extras=X_CONFIG | X_BLOCK_CHECKSUM, seconds=0.01, block_samples=50)[2])
     nb = len(blocks_of(base)) + len(blocks_of(small))
+    l0 = blocks_of(base)[0][1]
     dec = BatchDecoder(0)
     try:
         for shift in range(0, 34):
@@ -157,7 +158,7 @@ def test_device_checksum_at_every_slab_alignment():
             slab[o2:o2 + len(small)] = np.frombuffer(small, dtype=np.uint8)
             damaged = shift % 3 == 1
             if damaged:
-                slab[shift + 33] ^= 0x10
+                slab[shift + l0 - 40] ^= 0x10  # inside block 0's audio bitstream
             corpus = Corpus(slab, [shift, o2], [len(base), len(small)], out_format=N.OUT_PCM)
             assert corpus.nblocks == nb
             _out, results = dec.decode_corpus(corpus)

@@ -232,3 +232,49 @@ def test_packed_pcm_at_unaligned_output_offsets(gpu, kw):
             assert not any(r.rflags for r in results)
     finally:
         dec.close()
+
+
+@pytest.mark.parametrize("terms", [None, [18, 2, 18, 3, -2], [18, 17]], ids=["stock_in_register", "generic", "ff_fastest_in_register"])
+def test_staged_16bit_stereo_output_writes_only_its_own_bytes(gpu, terms):
+    """16-bit stereo PCM leaves the device through the shared-memory staging ring (wvb_pcm.cuh Stage16): full 32-byte
+    sectors where a block owns them, single words where a sector is shared with the neighbouring block, a gap or the slab
+    end.  Files of every length modulo 8 and tiny blocks put block starts at all eight sector phases inside one warp;
+    damaged files stop early (fault, short get_words); the bytes between the files' outputs must stay untouched."""
+    import torch
+    from wavpackdecoder_b200.batch import BatchDecoder, Corpus
+    kw = dict() if terms is None else dict(terms=terms, deltas=[2] * len(terms))
+    files, rng = [], np.random.default_rng(3)
+    for k, n in enumerate([1, 2, 7, 8, 9, 15, 16, 17, 23, 24, 25, 31, 33, 100, 1001, 2049, 4099, 5000, 7777, 12345]):
+        bs = [37, 1000, 4096, 22050][k % 4]
+        files.append(bytes(make_file(seed=0xA0 + k, nsamples=n, block_samples=bs, **kw)[2]))
+    for k in range(6):  # damaged: bit flips in the audio and a truncation
+        data = bytearray(make_file(seed=0xB0 + k, nsamples=9000 + 11 * k, block_samples=1500, **kw)[2])
+        if k < 5:
+            data[int(rng.integers(200, len(data) - 8))] ^= 1 << int(rng.integers(0, 8))
+        else:
+            del data[len(data) - 700:]
+        files.append(bytes(data))
+    corpus = Corpus.from_files(files, out_format=gpu.OUT_PCM)
+    # spread the files' outputs over the slab with odd gaps (multiples of 4 keep the one-word-per-frame kernel)
+    table = np.frombuffer(corpus.descs, dtype=np.uint64).reshape(-1, C.sizeof(gpu.BlockDesc) // 8)
+    shifts = np.cumsum(4 * rng.integers(1, 12, size=corpus.nfiles)).astype(np.uint64)
+    table[:corpus.nblocks, 1] += np.repeat(shifts, corpus.count.astype(np.int64))
+    total = int(corpus.out_bytes + shifts[-1] + 64)
+    d_out = torch.full((total + 64,), 0xEE, dtype=torch.uint8, device="cuda")
+    results = (gpu.BlockResult * corpus.nblocks)()
+    dec = BatchDecoder(0)
+    try:
+        dec.decode(corpus.slab.ctypes.data, corpus.slab.size, corpus.descs, corpus.nblocks, d_out.data_ptr(), total, gpu.OUT_PCM, gpu.OUT_DEVICE, results)
+    finally:
+        dec.close()
+    got = d_out.cpu().numpy()
+    untouched = np.ones(got.size, dtype=bool)
+    for i, data in enumerate(files):
+        ref, errs, status, info = oracle_decode(data, 0, 4096)
+        want = format_samples(ref, info["bytes_per_sample"])
+        lo = int(corpus.file_out_offset[i] + shifts[i])
+        f, c = int(corpus.first[i]), int(corpus.count[i])
+        if not any(results[k].rflags & gpu.RF_INEXACT for k in range(f, f + c)):
+            assert np.array_equal(got[lo:lo + want.size], want), i
+        untouched[lo:lo + want.size] = False
+    assert (got[untouched] == 0xEE).all()

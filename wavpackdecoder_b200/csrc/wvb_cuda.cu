@@ -28,6 +28,9 @@ namespace {
 #ifndef WVB_CTA
 #define WVB_CTA 128
 #endif
+#ifndef WVB_STAGE_OUTPUT
+#define WVB_STAGE_OUTPUT 1 // 0: experiment builds without the shared-memory output staging of the 16-bit stereo kernels
+#endif
 constexpr int CTA_THREADS = WVB_CTA;
 
 thread_local std::string g_last_error;
@@ -44,28 +47,45 @@ int set_error(int code, const std::string &msg)
 
 struct Launch { int variant; int cls; uint32_t first, count; };
 
-struct SharedColumn { // word i of this thread's column; [slot][thread] layout
-    int *base;
-    __device__ __forceinline__ int &operator()(int i) { return base[i * CTA_THREADS]; }
-    __device__ __forceinline__ int cap() const // words per thread this launch's dynamic shared memory provides
+// Dynamic shared memory of a decode CTA: cls words per thread laid out [slot][thread] (a thread's "column": bank == lane
+// for any per-lane slot index), then, for the kernels that stage their output (16-bit stereo PCM, wvb_pcm.cuh Stage16),
+// 16 bytes of staging bookkeeping per thread.  RESERVE: column slots at the top kept for the staging ring (the generic
+// decorrelator's state lives in the column during the sample loop; the in-register kernels' state is dead by then and the
+// ring reuses slots 0..15).
+template <int CTA, bool STAGED = false, int RESERVE = 0> struct SharedColumn {
+    static constexpr int kThreads = CTA;
+    static constexpr bool kStaged = STAGED;
+    int *base;   // this thread's column
+    int *origin; // word 0 of the CTA's dynamic shared memory
+    __device__ __forceinline__ int &operator()(int i) { return base[i * CTA]; }
+    __device__ __forceinline__ int slots() const // column slots this launch's dynamic shared memory provides
     {
         uint32_t bytes;
         asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(bytes));
-        return (int)(bytes / (CTA_THREADS * sizeof(int)));
+        return (int)((bytes - (STAGED ? CTA * 16u : 0u)) / (CTA * sizeof(int)));
     }
+    __device__ __forceinline__ int cap() const { return slots() - RESERVE; } // slots for decorrelation state
+    __device__ __forceinline__ int ring_slot0() const { return RESERVE ? cap() : 0; }
+    __device__ __forceinline__ uint4 *stage_meta() const { return (uint4 *)(origin + slots() * CTA); } // [thread]
 };
 
-template <bool STEREO, bool HYB, bool GENFIX, class DEC, int MINB = 0, bool F16 = false>
-__global__ void __launch_bounds__(CTA_THREADS, MINB)
+// CTA: threads per CTA.  Nothing in the decoder is CTA-wide (no barrier, no shared data between threads), so the CTA size
+// only sets the granularity at which shared memory and registers are handed out: blocks with long term lists (150-250
+// words of decorrelation state per thread) get one-warp CTAs, which fit 10 warps per SM where 128-thread CTAs fit 8.
+constexpr int CTA_SMALL = 32;
+template <bool STEREO, bool HYB, bool GENFIX, class DEC, int MINB = 0, bool F16 = false, int CTA = CTA_THREADS>
+__global__ void __launch_bounds__(CTA, MINB)
 k_decode_pcm(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ descs, const uint32_t *__restrict__ order,
              uint32_t count, uint8_t *__restrict__ out, int out_format, wvb_block_result *__restrict__ results)
 {
     extern __shared__ int smem[];
-    const uint32_t i = blockIdx.x * CTA_THREADS + threadIdx.x;
+    const uint32_t i = blockIdx.x * CTA + threadIdx.x;
     const bool valid = i < count; // lanes past the end keep running (with no work): the decode loop is warp-synchronous
     const uint32_t bi = order[valid ? i : count - 1];
-    SharedColumn SM{smem + threadIdx.x};
-    wvb::decode_block_pcm<STEREO, HYB, GENFIX, SharedColumn, DEC, F16>(SM, in, descs[bi], out, out_format, &results[bi], valid);
+    constexpr bool staged = F16 && STEREO && !GENFIX && WVB_STAGE_OUTPUT;
+    using Column = SharedColumn<CTA, staged, (staged && !DEC::kFixed) ? wvb::STAGE_RING_SLOTS : 0>;
+    Column SM{smem + threadIdx.x, smem};
+    wvb::decode_block_pcm<STEREO, HYB, GENFIX, Column, DEC, F16>(SM, in, descs[bi], out, out_format, &results[bi], valid);
 }
 
 using GenS = wvb::GenericDecorr<true>;
@@ -140,6 +160,21 @@ template <class T> int ensure(T *&p, size_t &cap, size_t need)
 
 typedef void (*pcm_kernel_t)(const uint8_t *, const wvb_block_desc *, const uint32_t *, uint32_t, uint8_t *, int, wvb_block_result *);
 
+// the one-warp-CTA builds of the generic kernels (large shared-memory classes)
+pcm_kernel_t pcm_kernel_small(int variant)
+{
+    switch (variant) {
+    case wvb::V_MONO: return k_decode_pcm<false, false, false, GenM, 0, false, CTA_SMALL>;
+    case wvb::V_STEREO: return k_decode_pcm<true, false, false, GenS, 0, false, CTA_SMALL>;
+    case wvb::V_STEREO | wvb::V_F16: return k_decode_pcm<true, false, false, GenS, 0, true, CTA_SMALL>;
+    case wvb::V_MONO | wvb::V_GENFIX: return k_decode_pcm<false, false, true, GenM, 0, false, CTA_SMALL>;
+    case wvb::V_STEREO | wvb::V_GENFIX: return k_decode_pcm<true, false, true, GenS, 0, false, CTA_SMALL>;
+    case wvb::V_MONO | wvb::V_GENFIX | wvb::V_HYBRID: return k_decode_pcm<false, true, true, GenM, 0, false, CTA_SMALL>;
+    case wvb::V_STEREO | wvb::V_GENFIX | wvb::V_HYBRID: return k_decode_pcm<true, true, true, GenS, 0, false, CTA_SMALL>;
+    default: return nullptr;
+    }
+}
+
 pcm_kernel_t pcm_kernel(int variant, uint32_t count = 0, int sm_count = 148)
 {
     switch (variant) {
@@ -173,12 +208,14 @@ pcm_kernel_t pcm_kernel(int variant, uint32_t count = 0, int sm_count = 148)
 }
 
 // shared-memory size classes (words per thread); a launch uses the smallest class that fits its blocks
-const int kSmemClasses[] = {8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 128, 160, 192, 256, 320, 448};
+const int kSmemClasses[] = {8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 128};
+constexpr int SMEM_CLASS_MAX = 448, SMEM_CLASS_SMALL_CTA = 128; // classes above 128 words: steps of 8, one-warp CTAs
 int smem_class(int words)
 {
     for (int c : kSmemClasses)
         if (words <= c) return c;
-    return -1;
+    const int c = (words + 7) & ~7;
+    return c <= SMEM_CLASS_MAX ? c : -1;
 }
 
 // Sort blocks so that warps are homogeneous; emit one launch per (variant, smem class).
@@ -194,7 +231,9 @@ void make_plan(const wvb_block_desc *descs, size_t n, int fmt, std::vector<uint3
         int v = wvb::variant_of(d);
         // 16-bit interleaved stereo PCM gets its own launches: one aligned word store per frame, no byte-packing state
         if ((v & ~(wvb::V_FIXED | wvb::V_FIXED_B | wvb::V_FIXED_C)) == wvb::V_STEREO && wvb::block_is_fast16(d, fmt == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : fmt)) v |= wvb::V_F16;
-        int cls = v == wvb::V_DSD ? wvb::dsd_mode_class(d) : smem_class(d.smem_words);
+        // (the staged-output kernels keep a 16-slot ring in the column; the in-register ones reuse dead state slots for it)
+        const bool ring_in_class = WVB_STAGE_OUTPUT && (v & wvb::V_F16) && !(v & (wvb::V_FIXED | wvb::V_FIXED_B | wvb::V_FIXED_C));
+        int cls = v == wvb::V_DSD ? wvb::dsd_mode_class(d) : smem_class(std::max<int>(d.smem_words + (ring_in_class ? wvb::STAGE_RING_SLOTS : 0), (WVB_STAGE_OUTPUT && (v & wvb::V_F16)) ? wvb::STAGE_RING_SLOTS : 0));
         uint64_t clsbits = (uint64_t)(cls < 0 ? 1023 : cls) & 1023;
         // variant | class | term signature (16 bits) | inverted length (so long blocks start first)
         // variant (8 bits) | class (10) | term signature (16) | inverted length (30; longer blocks saturate, they only lose their order)
@@ -424,12 +463,19 @@ static int launch_plan(wvb_batch *b, const std::vector<Launch> &plan, const uint
             continue;
         }
         pcm_kernel_t k = pcm_kernel(L.variant, L.count, b->sm_count);
-        if (!k || L.cls <= 0 || L.cls > 448) return set_error(WVB_E_ARG, "block needs more decorrelation state than any kernel class provides");
-        size_t smem = (size_t)L.cls * CTA_THREADS * sizeof(int);
+        int cta = CTA_THREADS;
+        if (L.cls > SMEM_CLASS_SMALL_CTA) {
+            pcm_kernel_t ks = pcm_kernel_small(L.variant);
+            if (ks) { k = ks; cta = CTA_SMALL; }
+        }
+        if (!k || L.cls <= 0 || L.cls > SMEM_CLASS_MAX) return set_error(WVB_E_ARG, "block needs more decorrelation state than any kernel class provides");
+        size_t smem = (size_t)L.cls * cta * sizeof(int) + ((WVB_STAGE_OUTPUT && (L.variant & wvb::V_F16)) ? (size_t)cta * 16 : 0);
         if (smem > b->smem_optin) return set_error(WVB_E_ARG, "shared memory class exceeds the device limit");
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        unsigned grid = (L.count + CTA_THREADS - 1) / CTA_THREADS;
-        k<<<grid, CTA_THREADS, smem, s>>>(din, b->d_descs, b->d_order + L.first, L.count, dout, fmt == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : fmt, dres);
+        // (left alone, the driver sizes the shared-memory carve-out for fewer CTAs than the state allows)
+        if (cta == CTA_SMALL) CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        unsigned grid = (L.count + cta - 1) / cta;
+        k<<<grid, cta, smem, s>>>(din, b->d_descs, b->d_order + L.first, L.count, dout, fmt == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : fmt, dres);
         CUDA_TRY(cudaGetLastError());
         b->launches++;
     }

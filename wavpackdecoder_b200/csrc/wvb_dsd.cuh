@@ -26,8 +26,15 @@ constexpr int DSD_RAW_THREADS = 128;
 constexpr int DSD_HIGH_THREADS = 64;
 constexpr int DSD_FAST_WARPS = 4;
 
-struct PtableColumn { // ptable entry i of this thread: [256][DSD_HIGH_THREADS]
+// The adaptive table of mode 3: one 256-entry table per thread, [256][DSD_HIGH_THREADS] in shared memory (bank == lane).
+// It is what limits the kernel to 6 resident warps per SM.  Measured and rejected in round 2: entries packed to 24 bits
+// (entry - 0x10000 fits: a 16-bit plane and an 8-bit plane, 768 B per thread, 8-9 warps) with 64 / 96 / 128-thread CTAs:
+// 268 / 259 / 267 ms against 254 ms for this layout -- the second load and store per bit and the smaller L1 that the extra
+// shared memory leaves cost what the occupancy returns; one-warp CTAs: 363 ms.
+constexpr size_t DSD_HIGH_SMEM = (size_t)256 * DSD_HIGH_THREADS * sizeof(int);
+struct PtableColumn { // ptable entry i of this thread
     int *base;
+    __device__ __forceinline__ explicit PtableColumn(void *smem, int tid) : base((int *)smem + tid) {}
     __device__ __forceinline__ int &operator()(int i) { return base[i * DSD_HIGH_THREADS]; }
 };
 
@@ -174,7 +181,7 @@ k_dsd_high(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ de
     const bool valid = i < count;
     const uint32_t bi = order[valid ? i : count - 1];
     const wvb_block_desc &D = descs[bi];
-    PtableColumn PT{dsd_smem + threadIdx.x};
+    PtableColumn PT(dsd_smem, (int)threadIdx.x);
     dsd_decode_high(PT, ptables + 256 * dsd_key_rate(D.smem_words), in, D, out, out_format, &results[bi], valid);
 }
 
@@ -360,7 +367,7 @@ inline int launch_dsd(int cls, const uint8_t *din, const wvb_block_desc *d_descs
     } else if (cls == 3) {
         const int *pt = dsd_device_ptables(device);
         if (!pt) return WVB_E_CUDA;
-        const size_t smem = (size_t)256 * DSD_HIGH_THREADS * sizeof(int);
+        const size_t smem = DSD_HIGH_SMEM;
         if (smem > smem_optin) return WVB_E_ARG;
         if (cudaFuncSetAttribute((const void *)k_dsd_high, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return WVB_E_CUDA;
         k_dsd_high<<<(count + DSD_HIGH_THREADS - 1) / DSD_HIGH_THREADS, DSD_HIGH_THREADS, smem, s>>>(din, d_descs, d_order, count, dout, out_format, dres, pt);

@@ -21,35 +21,72 @@ WVB_DEV int dsd_key_hbits(uint32_t k) { return (int)((k >> 4) & 15u); }
 WVB_DEV int dsd_key_rate(uint32_t k) { return (int)((k >> 8) & 255u); }
 
 // sequential byte source over the ID_DSD_BLOCK payload with the reference's `byteptr < data.Length` guards.
-// One thread per stream: bytes come out of a 32-bit word fetched one word ahead (the range decoder consumes a byte
-// every few steps; a dependent byte load per renormalisation would put an L2 round trip on the critical path).
+// One thread per stream.  The stream is held as two aligned 32-bit words (the one with byte `pos` and the next) plus a
+// bit offset, the second word fetched one word ahead: the range decoder consumes a byte every few steps, and a dependent
+// byte load per renormalisation would put an L2 round trip on the critical path.  take()/skip() hand out up to four
+// bytes at once without a loop, so that 32 lanes renormalising by different amounts stay converged.
+#ifdef __CUDA_ARCH__
+static __device__ __forceinline__ uint32_t wvb_fshr(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }         // sh 0..31
+static __device__ __forceinline__ uint32_t wvb_fshl_clamp(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_lc(lo, hi, sh); } // sh 0..32
+static __device__ __forceinline__ uint32_t wvb_bswap(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+#else
+static inline uint32_t wvb_fshr(uint32_t lo, uint32_t hi, uint32_t sh) { return sh ? (lo >> sh) | (hi << (32 - sh)) : lo; }
+static inline uint32_t wvb_fshl_clamp(uint32_t lo, uint32_t hi, uint32_t sh) { return sh == 0 ? hi : sh >= 32 ? lo : (hi << sh) | (lo >> (32 - sh)); }
+static inline uint32_t wvb_bswap(uint32_t x) { return __builtin_bswap32(x); }
+#endif
+
 struct ByteReader {
-    const uint8_t *p;
-    uint32_t pos, len;
-    uint32_t cur, nxt;      // word holding byte `pos`, and the following word
-    const uint8_t *wnext;   // aligned address of the word after nxt
+    uint32_t pos, len;      // next byte of the payload, payload length
+    uint32_t cur, nxt;      // the aligned word holding byte `pos`, and the following word
+    uint32_t ahead;         // the word after nxt, requested one refill early: no consumer ever waits for a load just issued
+    uint32_t sh;            // bit offset of byte `pos` inside cur: 0, 8, 16 or 24
+    const uint8_t *wnext;   // aligned address of the word after `ahead`
     WVB_DEV uint32_t fetch()
     {
-        const uint32_t w = wvb_ld_u32(wnext); // the slab is padded: reading up to 8 bytes past the payload is safe
+        const uint32_t w = wvb_ld_u32(wnext); // the slab is padded: reading up to 12 bytes past the payload is safe
         wnext += 4;
         return w;
     }
     WVB_DEV void init(const uint8_t *s, uint32_t n, uint32_t at)
     {
-        p = s; len = n; pos = at;
+        len = n; pos = at;
         const uint8_t *a = s + at;
-        wnext = a - ((uintptr_t)a & 3);
+        const uint32_t mis = (uint32_t)((uintptr_t)a & 3);
+        wnext = a - mis;
+        sh = 8 * mis;
         cur = fetch();
         nxt = fetch();
+        ahead = fetch();
     }
     WVB_DEV bool more() const { return pos < len; }
     WVB_DEV uint32_t left() const { return len - pos; }
+    // the next four bytes with the FIRST one in the top bits: what four rounds of `v = (v << 8) | byte` assemble
+    WVB_DEV uint32_t peek4() const { return wvb_bswap(wvb_fshr(cur, nxt, sh)); }
+    WVB_DEV void skip(uint32_t k) // 0 <= k <= 4 bytes
+    {
+        pos += k;
+        sh += 8 * k;
+#ifdef __CUDA_ARCH__
+        // predicated, and written out so that the load lands in `ahead` itself (see BitReader::refill: left to the compiler
+        // the word goes through a temporary, and the copy out of it waits for the load)
+        asm volatile("{\n\t"
+                     ".reg .pred p;\n\t"
+                     "setp.ge.u32 p, %3, 32;\n\t"
+                     "@p mov.u32 %0, %1;\n\t"
+                     "@p mov.u32 %1, %2;\n\t"
+                     "@p ld.global.nc.u32 %2, [%4];\n\t"
+                     "@p add.u64 %4, %4, 4;\n\t"
+                     "@p sub.u32 %3, %3, 32;\n\t"
+                     "}"
+                     : "+r"(cur), "+r"(nxt), "+r"(ahead), "+r"(sh), "+l"(wnext));
+#else
+        if (sh >= 32) { cur = nxt; nxt = ahead; ahead = fetch(); sh -= 32; }
+#endif
+    }
     WVB_DEV uint32_t get()
     {
-        const uint32_t sh = (uint32_t)((uintptr_t)(p + pos) & 3) * 8;
-        const uint32_t b = (cur >> sh) & 0xffu;
-        pos++;
-        if (sh == 24) { cur = nxt; nxt = fetch(); }
+        const uint32_t b = peek4() >> 24;
+        skip(1);
         return b;
     }
 };
@@ -144,31 +181,37 @@ struct DsdFilt { int value, f0, f1, f2, f3, f4, f5, f6, factor, bytei; };
 struct RangeDec {
     uint32_t low, high, value;
     ByteReader br;
-    WVB_DEV void normalize() // DsdUtils.cs:424-429
+    // DsdUtils.cs:424-429: `while (((high ^ low) & 0xFF000000) == 0 && more) { shift one byte in }`.  After j rounds the
+    // top byte of high ^ low is byte j (from the top) of the ORIGINAL xor, and after four rounds the xor is all ones, so the
+    // loop runs min(leading zero bytes of high ^ low, bytes left) times: one count, three funnel shifts, no branch.
+    WVB_DEV void normalize()
     {
-        while (((high ^ low) & 0xFF000000u) == 0 && br.more()) {
-            value = (value << 8) | br.get();
-            high = (high << 8) | 0xFFu;
-            low <<= 8;
-        }
+        uint32_t k = (uint32_t)wvb_clz(high ^ low) >> 3; // 0..4
+        const uint32_t left = br.left();
+        if (k > left) k = left;
+        const uint32_t s8 = 8 * k;
+        value = wvb_fshl_clamp(br.peek4(), value, s8);
+        high = wvb_fshl_clamp(0xFFFFFFFFu, high, s8);
+        low = wvb_fshl_clamp(0u, low, s8);
+        br.skip(k);
     }
 };
+
+// adaptive probability table access: PT(i) for a plain int column; wvb_dsd.cuh overloads these for its packed column
+template <class SMEM> WVB_DEV int pt_load(SMEM &PT, int i) { return PT(i); }
+template <class SMEM> WVB_DEV void pt_store(SMEM &PT, int i, int v) { PT(i) = v; }
 
 template <class SMEM> WVB_DEV void dsd_high_bit(SMEM &PT, RangeDec &rc, DsdFilt &s) // DsdUtils.cs:408-441
 {
     const int pp = (s.value >> 8) & 255;
-    int pt = PT(pp);
+    int pt = pt_load(PT, pp);
     const uint32_t split = rc.low + ((rc.high - rc.low) >> 8) * ((uint32_t)pt >> 16);
-    if (rc.value <= split) {
-        rc.high = split;
-        pt += (DSD_UP - pt) >> 8;
-        s.f0 = -1;
-    } else {
-        rc.low = split + 1;
-        pt += (DSD_DOWN - pt) >> 8;
-        s.f0 = 0;
-    }
-    PT(pp) = pt;
+    const bool one = rc.value <= split; // (selects, not branches: the lanes of a warp decode different streams)
+    rc.high = one ? split : rc.high;
+    rc.low = one ? rc.low : split + 1;
+    pt += ((one ? (int)DSD_UP : (int)DSD_DOWN) - pt) >> 8;
+    s.f0 = one ? -1 : 0;
+    pt_store(PT, pp, pt);
     rc.normalize();
     s.value += s.f6 * 8;
     s.bytei = (int)((uint32_t)s.bytei << 1) | (s.f0 & 1);
@@ -194,7 +237,7 @@ WVB_DEV void dsd_decode_high(SMEM &PT, const int *ptable0, const uint8_t *in, co
     const uint8_t *p = in + D.in_offset + D.sub_off[WVB_SUB_DSD];
     const bool stereo = o.coded_ch == 2;
     const uint32_t n = valid ? D.block_samples : 0;
-    for (int i = 0; i < 256; ++i) PT(i) = ptable0[i];
+    for (int i = 0; i < 256; ++i) pt_store(PT, i, ptable0[i]);
     RangeDec rc;
     rc.br.init(p, D.sub_len[WVB_SUB_DSD], 4); // rate_shift, mode, rate_i, rate_s
     DsdFilt sp[2];

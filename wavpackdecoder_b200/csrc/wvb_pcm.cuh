@@ -400,6 +400,9 @@ WVB_DEV int upd_weight_clip(int w, int delta, int s, int in) // UnpackUtils.cs:7
 WVB_DEV uint32_t pack_pass(int term, int delta, int mask, int base) { return (uint32_t)(term + 5) | ((uint32_t)delta << 5) | ((uint32_t)mask << 8) | ((uint32_t)base << 16); }
 WVB_DEV int ring_mask(int term) { return term > 8 ? 1 : term < 0 ? 0 : term <= 1 ? 0 : term <= 2 ? 1 : term <= 4 ? 3 : 7; }
 
+// (Measured and rejected in round 2: a software-pipelined pass loop -- descriptor, weights and history of pass p+1 loaded
+// before the arithmetic of pass p, so that the shared-memory round trips leave the a/b dependency chain.  16-term lists at
+// 8-10 resident warps: 171 vs 152 ms; 5-term lists: 119 vs 100 ms.  The extra instructions cost more than the latency.)
 // SM(i): word i of this thread's private shared-memory column
 template <bool STEREO, class SMEM> WVB_DEV void decorr_frame(SMEM &SM, int nterms, uint32_t t, int &a, int &b)
 {
@@ -777,6 +780,77 @@ struct OutWriter {
     }
 };
 
+// ---- staged output of 16-bit stereo PCM (one aligned 32-bit word per frame) --------------------
+// A store instruction of this decoder writes 32 different output streams, 4 bytes each.  L2 does not hold on to such
+// partially written 32-byte sectors: ncu (round 2, profiles/r02_l2_write_path.txt) shows 52 % of the store sectors missing
+// in L2 (8 stores per sector would miss once, 12.5 %), every miss filling the sector from DRAM and every eviction writing
+// it back -- DRAM traffic 1.47x the algorithmic bytes, all of the excess on the output side.  So the words go through
+// shared memory instead: each lane appends its word to a 16-word ring in its own column (a shared store in place of the
+// global one), and every 8 frames the warp turns the rings into full-sector stores: two lanes per stream, 16 bytes each,
+// one st.global.v4 covering 16 complete 32-byte sectors.  Frames of all lanes advance together, so in units of output
+// words counted from each stream's sector-aligned base (W = phase + t) the same sector index completes for every lane at
+// the same iteration, whatever the stream's phase.  Only words of this block are written: a first or last sector shared
+// with the neighbouring block in the slab, or cut short by a fault, goes out word by word.
+constexpr int STAGE_RING_SLOTS = 16;
+#ifdef __CUDA_ARCH__
+template <class SMEM> struct Stage16 {
+    static constexpr uint32_t ROW = (uint32_t)SMEM::kThreads * 4u; // bytes between consecutive slots of a column
+    static constexpr uint32_t RING = (uint32_t)STAGE_RING_SLOTS * ROW;
+    char *ring;   // slot 0 of the ring rows (CTA-wide address; a thread's word of slot k is at ring + k*ROW + 4*tid)
+    uint4 *meta;  // [thread]: x,y = sector-aligned address of the stream's word W = 0; z = phase (W of frame 0); w = limit (first W not to write)
+    uint32_t x;   // ring offset of the slot the next frame goes to, with this thread's 4*tid folded into the low bits
+
+    __device__ __forceinline__ void init(SMEM &SM, uint8_t *op, uint32_t n)
+    {
+        ring = (char *)(SM.origin + SM.ring_slot0() * SMEM::kThreads);
+        meta = SM.stage_meta();
+        const uint64_t a = (uint64_t)(uintptr_t)op;
+        const uint32_t phase = (uint32_t)(a >> 2) & 7u;
+        x = phase * ROW + 4u * threadIdx.x;
+        meta[threadIdx.x] = make_uint4((uint32_t)(a & ~31ull), (uint32_t)(a >> 32), phase, phase + n);
+    }
+    __device__ __forceinline__ void push(uint32_t word)
+    {
+        *(uint32_t *)(ring + x) = word;
+        x = (x + ROW) & (RING - 1u); // (4*tid < ROW: the low bits pass through)
+    }
+    // frames t, t+1, ... of this lane are not written (fault / short get_words): the flush stops at what was produced
+    __device__ __forceinline__ void stop_at(uint32_t t)
+    {
+        uint32_t *m = (uint32_t *)&meta[threadIdx.x];
+        m[3] = m[2] + t;
+    }
+    // write out sector q (words 8q .. 8q+7) of all 32 streams of the warp; every lane of the warp must call it
+    __device__ __forceinline__ void flush(uint32_t q)
+    {
+        __syncwarp();
+        // (read through a volatile asm: the lane-dependent addresses below are loop invariants, and hoisted out of the sample
+        // loop they would hold registers the 80-register build does not have)
+        uint32_t tid;
+        asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+        const uint32_t lane = tid & 31u, wbase = tid & ~31u;
+#pragma unroll
+        for (uint32_t r = 0; r < 2; ++r) {
+            const uint32_t s = wbase + (lane >> 1) + 16u * r; // the stream (thread of this warp) whose half sector this lane moves
+            const uint32_t lo = 8u * q + 4u * (lane & 1u);    // first word of the half
+            const uint4 m = meta[s];
+            const char *src = ring + (lo & 15u) * ROW + 4u * s;
+            const uint32_t w0 = *(const uint32_t *)src, w1 = *(const uint32_t *)(src + ROW), w2 = *(const uint32_t *)(src + 2 * ROW),
+                           w3 = *(const uint32_t *)(src + 3 * ROW);
+            uint8_t *dst = (uint8_t *)(uintptr_t)(((uint64_t)m.y << 32) | m.x) + 4ull * lo;
+            if (lo >= m.z && lo + 4u <= m.w)
+                *(uint4 *)dst = make_uint4(w0, w1, w2, w3);
+            else if (lo + 4u > m.z && lo < m.w) { // a sector shared with the neighbouring block, or the block's last words
+                if (lo >= m.z && lo < m.w) *(uint32_t *)dst = w0;
+                if (lo + 1u >= m.z && lo + 1u < m.w) *(uint32_t *)(dst + 4) = w1;
+                if (lo + 2u >= m.z && lo + 2u < m.w) *(uint32_t *)(dst + 8) = w2;
+                if (lo + 3u >= m.z && lo + 3u < m.w) *(uint32_t *)(dst + 12) = w3;
+            }
+        }
+    }
+};
+#endif
+
 // The reference decodes a block in caller-sized pieces (one unpack_samples call each).  piece_bounds() recovers the piece
 // [ps, pe) that contains sample t from the descriptor's call grid (wvb_grid.h); it is evaluated only at piece events and on
 // faults, so the grid costs one register (the next event) in the sample loop.
@@ -974,6 +1048,11 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
     if (flags & F_HYBRID) mute_limit *= 2;
     const bool joint = STEREO && (flags & F_JOINT);
     constexpr bool fast16 = F16 && STEREO && !GENFIX;
+#ifdef __CUDA_ARCH__
+    constexpr bool staged = fast16 && SMEM::kStaged; // through shared memory, full-sector stores (Stage16)
+#else
+    constexpr bool staged = false;                   // the host emulation (tests/emul) stores directly
+#endif
     // the block's output is one contiguous byte run unless it is a channel pair inside wider frames (multichannel files)
     const bool packed = !fast16 && D.out_stride == out_ch && D.out_ch_offset == 0;
     const uint32_t unit_mask = unit == 4 ? 0xffffffffu : ((1u << (8 * unit)) - 1u);
@@ -992,6 +1071,10 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
     int crc = -1;
     bool fault = false, eof_fault = false;
     uint32_t fault_t = 0;
+#ifdef __CUDA_ARCH__
+    Stage16<SMEM> stage;
+    if constexpr (staged) stage.init(SM, op, n);
+#endif
     // All 32 lanes of a warp iterate together (warp-max trip count) and re-join at the top of every sample:
     // a lane left behind by a divergent branch must not be allowed to run the rest of its block alone.
     const uint32_t nmax = wvb_warp_max(n);
@@ -1014,7 +1097,11 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
                 if (!got) {           // get_words came back short (WordsUtils.cs:323,383,393): the reference still runs the
                     eof_fault = true; // passes and the CRC over the rest of the chunk, reading whatever the caller's buffer
                     a = b = 0;        // held.  We model those stale entries as zeros (exact for silence, and a CRC
-                }                     // mismatch either way otherwise).
+                                      // mismatch either way otherwise).
+#ifdef __CUDA_ARCH__
+                    if constexpr (staged) stage.stop_at(t);
+#endif
+                }
             }
             dec.frame(SM, nterms, t, a, b);
             if (joint) { b -= (a >> 1); a += b; } // UnpackUtils.cs:615 (App. E-9)
@@ -1025,7 +1112,12 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
                 if (STEREO) crc = crc * 3 + b;
                 if (!eof_fault) {
                     if constexpr (fast16) {
-                        *(uint32_t *)op = ((uint32_t)shl32(a, fx.shift) & 0xffffu) | ((uint32_t)shl32(b, fx.shift) << 16);
+                        const uint32_t word = ((uint32_t)shl32(a, fx.shift) & 0xffffu) | ((uint32_t)shl32(b, fx.shift) << 16);
+#ifdef __CUDA_ARCH__
+                        if constexpr (staged) stage.push(word);
+                        else
+#endif
+                            *(uint32_t *)op = word;
                     } else {
                         int va, vb = 0;
                         if (GENFIX) {
@@ -1054,9 +1146,22 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
                 fault = true;
                 fault_t = t;
                 live_n = 0;
+#ifdef __CUDA_ARCH__
+                if constexpr (staged) { if (!eof_fault) stage.stop_at(t); }
+#endif
             }
         }
+#ifdef __CUDA_ARCH__
+        if constexpr (staged) { if ((t & 7u) == 7u) stage.flush(t >> 3); } // (t is warp-uniform: every lane gets here)
+#endif
     }
+#ifdef __CUDA_ARCH__
+    if constexpr (staged) { // what the loop's flushes have not reached: at most 14 words per stream, in two sectors
+        stage.flush(nmax >> 3);
+        stage.flush((nmax >> 3) + 1u);
+        __syncwarp(); // the mute fill below may rewrite words other lanes have just stored for this lane
+    }
+#endif
 
     if (packed) ow.finish();
 

@@ -12,6 +12,7 @@ import struct
 import numpy as np
 
 from . import _native as N
+from . import containers
 from . import wavpack_utils as W
 from .batch import BatchDecoder, Corpus
 
@@ -41,14 +42,41 @@ def _context(corpus, i):
     return wpc
 
 
-def unpack_files(files, device=0, reference_quirks=True):
+def native_container(wpc, total_samples, nch, byteps):
+    """(header, trailer) of the container WavpackGetFileFormat names, for a file that stores no header of its own.
+    An extension over the reference, which writes RIFF/WAVE whatever the format (WvDemo.cs:76-105)."""
+    fmt = W.WavpackGetFileFormat(wpc)
+    rate, bits = W.WavpackGetSampleRate(wpc), W.WavpackGetBitsPerSample(wpc)
+    dsd = bool(wpc.info.is_dsd) if hasattr(wpc.info, "is_dsd") else W.WavpackGetFileFormat(wpc) in (containers.WP_FORMAT_DFF, containers.WP_FORMAT_DSF)
+    if fmt == containers.WP_FORMAT_WAV and not dsd:
+        return wave_header(total_samples, nch, rate, bits, byteps), b""
+    if fmt == containers.WP_FORMAT_W64 and not dsd:
+        return (containers.w64_header(total_samples, nch, rate, bits, byteps, bool(W.WavpackGetIsFloat(wpc))),
+                containers.w64_trailer(total_samples, nch, byteps))
+    if fmt == containers.WP_FORMAT_DFF and dsd:
+        return containers.dff_header(total_samples, nch, rate * 8), containers.dff_trailer(total_samples, nch)
+    raise NotImplementedError("no header synthesis for file format %d (%s audio): DSF and CAF need the samples re-laid-out" %
+                              (fmt, "DSD" if dsd else "PCM"))
+
+
+def unpack_files(files, device=0, reference_quirks=True, container="reference"):
     """Decode a list of .wv byte strings the way WvDemo.Main does.  Returns a list of (output file bytes, exit code).
+
+    container: "reference" writes what the demo writes (stored header, else RIFF/WAVE; DSD as offset-binary bytes);
+    "native" is an extension: a stored header always passes through, otherwise the header of the format the file names is
+    synthesised (WAV, W64, DFF: containers.py), DSD bytes stay raw, and the demo's short-file quirk does not apply.
 
     reference_quirks: files with fewer than 100 * SAMPLE_BUFFER_SIZE (409 600) samples, or of unknown length, make the reference demo throw
     DivideByZeroException at its progress print (`total_unpacked_samples % loop_samples`, WvDemo.cs:113,136) after the
     first chunk has been written: it leaves header + first chunk on disk and exits 1.  True reproduces that; False
     writes the complete file."""
-    corpus = Corpus.from_files(files, open_flags=0, chunk_samples=SAMPLE_BUFFER_SIZE, out_format=N.OUT_PCM)
+    if container not in ("reference", "native"):
+        raise ValueError("container must be 'reference' or 'native'")
+    native = container == "native"
+    if native:
+        reference_quirks = False
+    out_format = N.OUT_DSD_RAW if native else N.OUT_PCM
+    corpus = Corpus.from_files(files, open_flags=0, chunk_samples=SAMPLE_BUFFER_SIZE, out_format=out_format)
     nfiles = corpus.nfiles
     ctxs = [_context(corpus, i) for i in range(nfiles)]
     heads, tails, pcm_bytes, ok = [], [], [], []
@@ -59,13 +87,17 @@ def unpack_files(files, device=0, reference_quirks=True):
         nch = W.WavpackGetReducedChannels(wpc)
         byteps = W.WavpackGetBytesPerSample(wpc)
         header = W.WavpackGetHeader(wpc)
-        if header is not None and not W.WavpackGetIsFloat(wpc):  # WvDemo.cs:76-77
+        trailer = W.WavpackGetTrailer(wpc)  # WvDemo.cs:143-145
+        pad = b""
+        if header is not None and (native or not W.WavpackGetIsFloat(wpc)):  # WvDemo.cs:76-77
             heads.append(header)
+        elif native:
+            h, pad = native_container(wpc, int(wpc.info.indexed_samples), nch, byteps)
+            heads.append(h)
         else:
             heads.append(wave_header(W.WavpackGetNumSamples(wpc, True), nch, W.WavpackGetSampleRate(wpc),
                                      W.WavpackGetBitsPerSample(wpc), byteps))
-        trailer = W.WavpackGetTrailer(wpc)  # WvDemo.cs:143-145
-        tails.append(trailer if trailer is not None else b"")
+        tails.append(pad + (trailer if trailer is not None else b""))
         pcm_bytes.append(int(wpc.info.indexed_samples) * nch * byteps)
         ok.append(True)
 
@@ -88,7 +120,7 @@ def unpack_files(files, device=0, reference_quirks=True):
     if corpus.nblocks:
         dec = BatchDecoder(device)
         try:
-            dec.decode(corpus.slab.ctypes.data, corpus.slab.size, corpus.descs, corpus.nblocks, out.ctypes.data, total, N.OUT_PCM, 0, results)
+            dec.decode(corpus.slab.ctypes.data, corpus.slab.size, corpus.descs, corpus.nblocks, out.ctypes.data, total, out_format, 0, results)
         finally:
             dec.close()
 
