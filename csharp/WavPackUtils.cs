@@ -97,9 +97,12 @@ namespace WavPack
         [DllImport(Lib)] internal static extern unsafe int wvb_batch_md5(IntPtr batch, void* device_out, UIntPtr out_bytes, ulong* offsets, ulong* lengths,
             UIntPtr n, byte* digests);
         [DllImport(Lib)] internal static extern unsafe int wvb_stored_md5(byte* file, UIntPtr len, byte* md5);
+        // WavPack 5 block checksum (ID_BLOCK_CHECKSUM, which the reference only notes: MetadataUtils.cs:183): 1 matching, 0 wrong, -1 none.
+        // wvb_batch_decode checks every block that has one on the device and reports WVB_RF_BLOCK_CHECKSUM in its result flags
+        [DllImport(Lib)] internal static extern unsafe int wvb_block_checksum_ok(byte* block, UIntPtr len);
         internal const int WVB_ABI_VERSION = 2;
         internal const int WVB_OUT_INT32 = 0, WVB_OUT_PCM = 1;
-        internal const uint WVB_RF_CRC_ERROR = 1;
+        internal const uint WVB_RF_CRC_ERROR = 1, WVB_RF_BLOCK_CHECKSUM = 32;
         internal const int WVB_E_CAPACITY = -4;
     }
 

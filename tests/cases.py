@@ -177,6 +177,12 @@ def corrupt_cases():
     blm = _blocks(datam)
     out.append(("mono_flip", flip(datam, blm[1][0] + blm[1][1] // 2, 0x10), 0, 4096))
     out.append(("mono_flip_chunk777", flip(datam, blm[1][0] + blm[1][1] // 2, 0x10), 0, 777))
+    # quirk C-5 (UnpackUtils.cs:572-575): a magnitude fault in the first sample of a mono block that begins 1000 samples
+    # into the caller's call: buffer index 1000 + 0 == sample_count 1000, so the reference mutes nothing
+    cfg, src, datac5 = make_file(channels=1, seconds=0.3, block_samples=1000, terms=[18, 18, 2, 3], deltas=[2] * 4)
+    blc = _blocks(datac5)
+    for byte, bit, chunk in ((47, 0, 4096), (49, 4, 4096), (47, 4, 4096), (49, 4, 2000)):
+        out.append(("mono_fault_at_coincident_buffer_index_%d_%d_%d" % (byte, bit, chunk), flip(datac5, blc[1][0] + byte, 1 << bit), 0, chunk))
     cfg, src, datah = make_file(seconds=2.0, kind=1)
     blh = _blocks(datah)
     out.append(("hybrid_flip", flip(datah, blh[1][0] + blh[1][1] // 2, 0x10), 0, 4096))

@@ -104,7 +104,7 @@ def test_native_containers_on_device():
             chunks = parse_w64(blob)
             do, dl = chunks["data"]
             assert blob[do:do + dl] == format_samples(ref, info["bytes_per_sample"]).tobytes()
-            assert struct.unpack_from("<HHI", blob, chunks["fmt "][0]) == (1, info["channels"], info["sample_rate"])
+            assert struct.unpack_from("<HHI", blob, chunks["fmt "][0]) == (1, info["reduced_channels"], info["sample_rate"])
         elif kind in ("wav", "stored"):
             assert blob[:4] == b"RIFF" and blob[44:] == format_samples(ref, info["bytes_per_sample"]).tobytes()
         else:
@@ -113,6 +113,6 @@ def test_native_containers_on_device():
             assert blob[do:do + ds] == np.asarray(ref, dtype=np.uint8).tobytes()  # raw DSD bytes, not the demo's offset-binary
             po, ps = top[b"PROP"]
             prop = {cid: (o, s) for cid, o, s in parse_iff(blob, po + 4, po + ps)}
-            assert struct.unpack_from(">I", blob, prop[b"FS  "][0])[0] == info["sample_rate"] * 8
+            assert struct.unpack_from(">I", blob, prop[b"FS  "][0])[0] == info["sample_rate"]
     with pytest.raises(NotImplementedError):
         unpack_files([_with_file_format(dsd, K.WP_FORMAT_DSF)], container="native")

@@ -270,7 +270,11 @@ def test_staged_16bit_stereo_output_writes_only_its_own_bytes(gpu, terms):
     got = d_out.cpu().numpy()
     untouched = np.ones(got.size, dtype=bool)
     for i, data in enumerate(files):
-        ref, errs, status, info = oracle_decode(data, 0, 4096)
+        try:
+            ref, errs, status, info = oracle_decode(data, 0, 4096)
+        except RuntimeError:  # a flip that makes the file unopenable: no blocks, no output
+            assert int(corpus.count[i]) == 0
+            continue
         want = format_samples(ref, info["bytes_per_sample"])
         lo = int(corpus.file_out_offset[i] + shifts[i])
         f, c = int(corpus.first[i]), int(corpus.count[i])

@@ -49,7 +49,7 @@ struct Launch { int variant; int cls; uint32_t first, count; };
 
 // Dynamic shared memory of a decode CTA: cls words per thread laid out [slot][thread] (a thread's "column": bank == lane
 // for any per-lane slot index), then, for the kernels that stage their output (16-bit stereo PCM, wvb_pcm.cuh Stage16),
-// 16 bytes of staging bookkeeping per thread.  RESERVE: column slots at the top kept for the staging ring (the generic
+// 8 bytes of staging bookkeeping per thread.  RESERVE: column slots at the top kept for the staging ring (the generic
 // decorrelator's state lives in the column during the sample loop; the in-register kernels' state is dead by then and the
 // ring reuses slots 0..15).
 template <int CTA, bool STAGED = false, int RESERVE = 0> struct SharedColumn {
@@ -62,11 +62,11 @@ template <int CTA, bool STAGED = false, int RESERVE = 0> struct SharedColumn {
     {
         uint32_t bytes;
         asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(bytes));
-        return (int)((bytes - (STAGED ? CTA * 16u : 0u)) / (CTA * sizeof(int)));
+        return (int)((bytes - (STAGED ? CTA * 8u : 0u)) / (CTA * sizeof(int)));
     }
     __device__ __forceinline__ int cap() const { return slots() - RESERVE; } // slots for decorrelation state
     __device__ __forceinline__ int ring_slot0() const { return RESERVE ? cap() : 0; }
-    __device__ __forceinline__ uint4 *stage_meta() const { return (uint4 *)(origin + slots() * CTA); } // [thread]
+    __device__ __forceinline__ uint2 *stage_meta() const { return (uint2 *)(origin + slots() * CTA); } // [thread]
 };
 
 // CTA: threads per CTA.  Nothing in the decoder is CTA-wide (no barrier, no shared data between threads), so the CTA size
@@ -469,7 +469,7 @@ static int launch_plan(wvb_batch *b, const std::vector<Launch> &plan, const uint
             if (ks) { k = ks; cta = CTA_SMALL; }
         }
         if (!k || L.cls <= 0 || L.cls > SMEM_CLASS_MAX) return set_error(WVB_E_ARG, "block needs more decorrelation state than any kernel class provides");
-        size_t smem = (size_t)L.cls * cta * sizeof(int) + ((WVB_STAGE_OUTPUT && (L.variant & wvb::V_F16)) ? (size_t)cta * 16 : 0);
+        size_t smem = (size_t)L.cls * cta * sizeof(int) + ((WVB_STAGE_OUTPUT && (L.variant & wvb::V_F16)) ? (size_t)cta * 8 : 0);
         if (smem > b->smem_optin) return set_error(WVB_E_ARG, "shared memory class exceeds the device limit");
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // (left alone, the driver sizes the shared-memory carve-out for fewer CTAs than the state allows)

@@ -55,6 +55,12 @@ static inline uint32_t wvb_warp_max(uint32_t v) { return v; }
 
 namespace wvb {
 
+// (Measured and rejected, rounds 2a and 2b: moving the adds of constants to the integer FMA pipe.  tools/probe/pipe_probe.cu
+// shows the ALU pipe (IADD3, LOP3, SHF, SEL, ISETP, LEA) and the integer FMA pipe (IMAD) each issuing every other cycle,
+// independently (0.50 warp instructions per cycle per scheduler alone, 0.98 alternating), and this decoder has 263 ALU
+// against 135 FMA-pipe instructions per frame.  But x + c as IMAD needs the multiplier 1 in a vector register -- the
+// IMAD forms take one immediate, and not a uniform register together with one -- and at 80-90 registers the compiler
+// re-loads that 1 from constant memory next to every use: 82.0 vs 78.3 ms.)
 WVB_TABLE uint8_t k_log2[256] = WV_LOG2_TABLE_INIT;
 WVB_TABLE uint8_t k_exp2[256] = WV_EXP2_TABLE_INIT;
 
@@ -784,30 +790,34 @@ struct OutWriter {
 // A store instruction of this decoder writes 32 different output streams, 4 bytes each.  L2 does not hold on to such
 // partially written 32-byte sectors: ncu (round 2, profiles/r02_l2_write_path.txt) shows 52 % of the store sectors missing
 // in L2 (8 stores per sector would miss once, 12.5 %), every miss filling the sector from DRAM and every eviction writing
-// it back -- DRAM traffic 1.47x the algorithmic bytes, all of the excess on the output side.  So the words go through
-// shared memory instead: each lane appends its word to a 16-word ring in its own column (a shared store in place of the
-// global one), and every 8 frames the warp turns the rings into full-sector stores: two lanes per stream, 16 bytes each,
-// one st.global.v4 covering 16 complete 32-byte sectors.  Frames of all lanes advance together, so in units of output
-// words counted from each stream's sector-aligned base (W = phase + t) the same sector index completes for every lane at
-// the same iteration, whatever the stream's phase.  Only words of this block are written: a first or last sector shared
-// with the neighbouring block in the slab, or cut short by a fault, goes out word by word.
+// it back -- DRAM traffic 1.47x the algorithmic bytes, all of the excess on the output side.  So the words are staged in
+// shared memory: each lane appends its word to a 16-word ring in its own column (a shared store in place of the global
+// one), and every 8 frames reads one complete, 32-byte aligned sector of its own stream back and writes it with a single
+// 256-bit store -- a warp instruction then writes 32 whole sectors.  Frames of all lanes advance together, so counted in
+// output words from each stream's sector-aligned base (W = phase + t) the same sector index completes for every lane at
+// the same iteration, whatever the stream's phase: the flush is warp-uniform control flow.  Only words of this block are
+// written: a first or last sector shared with the neighbouring block in the slab, or cut short by a fault, goes out
+// word by word.  (A first version moved half sectors between lanes to build the stores, two lanes per stream and
+// st.global.v4: correct traffic, but 5-7 instructions per frame against 2 for this one.)
 constexpr int STAGE_RING_SLOTS = 16;
 #ifdef __CUDA_ARCH__
 template <class SMEM> struct Stage16 {
     static constexpr uint32_t ROW = (uint32_t)SMEM::kThreads * 4u; // bytes between consecutive slots of a column
     static constexpr uint32_t RING = (uint32_t)STAGE_RING_SLOTS * ROW;
-    char *ring;   // slot 0 of the ring rows (CTA-wide address; a thread's word of slot k is at ring + k*ROW + 4*tid)
-    uint4 *meta;  // [thread]: x,y = sector-aligned address of the stream's word W = 0; z = phase (W of frame 0); w = limit (first W not to write)
-    uint32_t x;   // ring offset of the slot the next frame goes to, with this thread's 4*tid folded into the low bits
+    char *ring;    // slot 0 of the ring rows (CTA-wide; this thread's word of slot k is at ring + k*ROW + 4*tid)
+    uint2 *meta;   // this thread's {phase = W of frame 0, limit = first W not to write}
+    uint8_t *base; // sector-aligned global address of the stream's word W = 0
+    uint32_t x;    // ring offset of the slot the next frame goes to, with this thread's 4*tid folded into the low bits
 
     __device__ __forceinline__ void init(SMEM &SM, uint8_t *op, uint32_t n)
     {
         ring = (char *)(SM.origin + SM.ring_slot0() * SMEM::kThreads);
-        meta = SM.stage_meta();
+        meta = (uint2 *)(SM.stage_meta() + threadIdx.x);
         const uint64_t a = (uint64_t)(uintptr_t)op;
         const uint32_t phase = (uint32_t)(a >> 2) & 7u;
+        base = (uint8_t *)(uintptr_t)(a & ~31ull);
         x = phase * ROW + 4u * threadIdx.x;
-        meta[threadIdx.x] = make_uint4((uint32_t)(a & ~31ull), (uint32_t)(a >> 32), phase, phase + n);
+        *meta = make_uint2(phase, phase + n);
     }
     __device__ __forceinline__ void push(uint32_t word)
     {
@@ -815,37 +825,25 @@ template <class SMEM> struct Stage16 {
         x = (x + ROW) & (RING - 1u); // (4*tid < ROW: the low bits pass through)
     }
     // frames t, t+1, ... of this lane are not written (fault / short get_words): the flush stops at what was produced
-    __device__ __forceinline__ void stop_at(uint32_t t)
-    {
-        uint32_t *m = (uint32_t *)&meta[threadIdx.x];
-        m[3] = m[2] + t;
-    }
-    // write out sector q (words 8q .. 8q+7) of all 32 streams of the warp; every lane of the warp must call it
+    __device__ __forceinline__ void stop_at(uint32_t t) { meta->y = meta->x + t; }
+    // write out sector q (words 8q .. 8q+7) of this lane's stream
     __device__ __forceinline__ void flush(uint32_t q)
     {
-        __syncwarp();
-        // (read through a volatile asm: the lane-dependent addresses below are loop invariants, and hoisted out of the sample
-        // loop they would hold registers the 80-register build does not have)
-        uint32_t tid;
-        asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
-        const uint32_t lane = tid & 31u, wbase = tid & ~31u;
-#pragma unroll
-        for (uint32_t r = 0; r < 2; ++r) {
-            const uint32_t s = wbase + (lane >> 1) + 16u * r; // the stream (thread of this warp) whose half sector this lane moves
-            const uint32_t lo = 8u * q + 4u * (lane & 1u);    // first word of the half
-            const uint4 m = meta[s];
-            const char *src = ring + (lo & 15u) * ROW + 4u * s;
+        const uint2 m = *meta;
+        const uint32_t lo = 8u * q;
+        const char *src = ring + (x & (ROW - 1u)) + (lo & 15u) * ROW;
+        uint8_t *dst = base + 32ull * q;
+        if (lo >= m.x && lo + 8u <= m.y) {
             const uint32_t w0 = *(const uint32_t *)src, w1 = *(const uint32_t *)(src + ROW), w2 = *(const uint32_t *)(src + 2 * ROW),
-                           w3 = *(const uint32_t *)(src + 3 * ROW);
-            uint8_t *dst = (uint8_t *)(uintptr_t)(((uint64_t)m.y << 32) | m.x) + 4ull * lo;
-            if (lo >= m.z && lo + 4u <= m.w)
-                *(uint4 *)dst = make_uint4(w0, w1, w2, w3);
-            else if (lo + 4u > m.z && lo < m.w) { // a sector shared with the neighbouring block, or the block's last words
-                if (lo >= m.z && lo < m.w) *(uint32_t *)dst = w0;
-                if (lo + 1u >= m.z && lo + 1u < m.w) *(uint32_t *)(dst + 4) = w1;
-                if (lo + 2u >= m.z && lo + 2u < m.w) *(uint32_t *)(dst + 8) = w2;
-                if (lo + 3u >= m.z && lo + 3u < m.w) *(uint32_t *)(dst + 12) = w3;
-            }
+                           w3 = *(const uint32_t *)(src + 3 * ROW), w4 = *(const uint32_t *)(src + 4 * ROW), w5 = *(const uint32_t *)(src + 5 * ROW),
+                           w6 = *(const uint32_t *)(src + 6 * ROW), w7 = *(const uint32_t *)(src + 7 * ROW);
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(w0), "r"(w1), "r"(w2), "r"(w3), "r"(w4),
+                         "r"(w5), "r"(w6), "r"(w7)
+                         : "memory");
+        } else if (lo + 8u > m.x && lo < m.y) { // a sector shared with the neighbouring block, or the block's last words
+#pragma unroll 1
+            for (uint32_t i = 0; i < 8; ++i)
+                if (lo + i >= m.x && lo + i < m.y) *(uint32_t *)(dst + 4 * i) = *(const uint32_t *)(src + i * ROW);
         }
     }
 };
@@ -1068,8 +1066,8 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
         next_ev = next_piece_event<STEREO>(0, ps, pe);
     }
 
-    int crc = -1;
-    bool fault = false, eof_fault = false;
+    int crc = -1, crc_keep = 0;
+    bool fault = false, eof_fault = false, crc_frozen = false;
     uint32_t fault_t = 0;
 #ifdef __CUDA_ARCH__
     Stage16<SMEM> stage;
@@ -1084,6 +1082,7 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
         const bool act = t < live_n;
         if (act) {
             if (t == next_ev) {
+                if (!STEREO && crc_frozen) { crc = crc_keep; crc_frozen = false; } // (mono: every event is a piece boundary)
                 dec.truncate(SM, nterms);
                 uint32_t ps, pe;
                 piece_bounds(D, n, t, ps, pe);
@@ -1107,6 +1106,25 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
             if (joint) { b -= (a >> 1); a += b; } // UnpackUtils.cs:615 (App. E-9)
             const int aa = a < 0 ? -a : a, ab = b < 0 ? -b : b;
             bool stop = aa > mute_limit || (STEREO && ab > mute_limit);
+            if constexpr (!STEREO) {
+                // Quirk C-5 (UnpackUtils.cs:572-575): the mono scan records the BUFFER index of the offending sample, which
+                // includes the samples the same call decoded before this block.  When that sum happens to equal the piece
+                // length, `i != sample_count` does not fire: nothing is muted, the scan (magnitude test and CRC) simply ended
+                // early, and the piece goes out as decoded.  The CRC resumes with the next piece.
+                if (stop) {
+                    if (crc_frozen) stop = false;
+                    else {
+                        uint32_t ps, pe;
+                        piece_bounds(D, n, t, ps, pe);
+                        const uint32_t before = call_lookback(D, ps) * (uint32_t)D.out_stride;
+                        if (before != 0 && before + (t - ps) == pe - ps) {
+                            crc_frozen = true;
+                            crc_keep = crc;
+                            stop = false;
+                        }
+                    }
+                }
+            }
             if (!stop) {
                 crc = crc * 3 + a;
                 if (STEREO) crc = crc * 3 + b;
@@ -1159,11 +1177,11 @@ WVB_DEV void decode_block_pcm(SMEM &SM, const uint8_t *in, const wvb_block_desc 
     if constexpr (staged) { // what the loop's flushes have not reached: at most 14 words per stream, in two sectors
         stage.flush(nmax >> 3);
         stage.flush((nmax >> 3) + 1u);
-        __syncwarp(); // the mute fill below may rewrite words other lanes have just stored for this lane
     }
 #endif
 
     if (packed) ow.finish();
+    if (crc_frozen) crc = crc_keep;
 
     if (fault) { // mute from the start of the caller chunk that contains the fault (UnpackUtils.cs:649-664, App. E-10)
         rflags |= WVB_RF_MUTED;

@@ -47,14 +47,14 @@ def native_container(wpc, total_samples, nch, byteps):
     An extension over the reference, which writes RIFF/WAVE whatever the format (WvDemo.cs:76-105)."""
     fmt = W.WavpackGetFileFormat(wpc)
     rate, bits = W.WavpackGetSampleRate(wpc), W.WavpackGetBitsPerSample(wpc)
-    dsd = bool(wpc.info.is_dsd) if hasattr(wpc.info, "is_dsd") else W.WavpackGetFileFormat(wpc) in (containers.WP_FORMAT_DFF, containers.WP_FORMAT_DSF)
+    dsd = bool(wpc.info.first_flags & 0x80000000)  # DSD_FLAG of the first audio block
     if fmt == containers.WP_FORMAT_WAV and not dsd:
         return wave_header(total_samples, nch, rate, bits, byteps), b""
     if fmt == containers.WP_FORMAT_W64 and not dsd:
         return (containers.w64_header(total_samples, nch, rate, bits, byteps, bool(W.WavpackGetIsFloat(wpc))),
                 containers.w64_trailer(total_samples, nch, byteps))
     if fmt == containers.WP_FORMAT_DFF and dsd:
-        return containers.dff_header(total_samples, nch, rate * 8), containers.dff_trailer(total_samples, nch)
+        return containers.dff_header(total_samples, nch, rate), containers.dff_trailer(total_samples, nch)  # (the getter already reports the one-bit rate)
     raise NotImplementedError("no header synthesis for file format %d (%s audio): DSF and CAF need the samples re-laid-out" %
                               (fmt, "DSD" if dsd else "PCM"))
 
