@@ -76,7 +76,7 @@ def build_corpus(nfiles, seconds, base_seed, threads, budget_s, pin, cfg_kw=None
     assert used > 0
     per_file = int(sizes.max())
     rate = probe_n / dt
-    unique = int(max(probe_n, min(nfiles, rate * budget_s)))
+    unique = int(min(nfiles, max(probe_n, min(nfiles, rate * budget_s))))
     slot = (int(per_file * 1.03) + 4096 + 63) & ~63
     total_cap = slot * nfiles + 4096
     slab_t = torch.empty(total_cap, dtype=torch.uint8, pin_memory=pin)

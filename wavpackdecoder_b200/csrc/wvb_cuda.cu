@@ -76,12 +76,14 @@ constexpr int CTA_SMALL = 32;
 template <bool STEREO, bool HYB, bool GENFIX, class DEC, int MINB = 0, bool F16 = false, int CTA = CTA_THREADS>
 __global__ void __launch_bounds__(CTA, MINB)
 k_decode_pcm(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ descs, const uint32_t *__restrict__ order,
-             uint32_t count, uint8_t *__restrict__ out, int out_format, wvb_block_result *__restrict__ results)
+             uint32_t count, uint8_t *__restrict__ out, int out_format, wvb_block_result *__restrict__ results, uint32_t spread)
 {
     extern __shared__ int smem[];
-    const uint32_t i = blockIdx.x * CTA + threadIdx.x;
-    const bool valid = i < count; // lanes past the end keep running (with no work): the decode loop is warp-synchronous
-    const uint32_t bi = order[valid ? i : count - 1];
+    // spread (a power-of-two exponent, 0..5): a launch too small to fill the GPU gives every block a group of 2^spread lanes
+    // and lets only the group's last lane work -- see pick_spread()
+    const uint32_t i = blockIdx.x * CTA + threadIdx.x, slot = i >> spread, gmask = (1u << spread) - 1u;
+    const bool valid = slot < count && (i & gmask) == gmask; // lanes without work keep running: the decode loop is warp-synchronous
+    const uint32_t bi = order[slot < count ? slot : count - 1];
     constexpr bool staged = F16 && STEREO && !GENFIX && WVB_STAGE_OUTPUT;
     using Column = SharedColumn<CTA, staged, (staged && !DEC::kFixed) ? wvb::STAGE_RING_SLOTS : 0>;
     Column SM{smem + threadIdx.x, smem};
@@ -158,7 +160,7 @@ template <class T> int ensure(T *&p, size_t &cap, size_t need)
     return WVB_OK;
 }
 
-typedef void (*pcm_kernel_t)(const uint8_t *, const wvb_block_desc *, const uint32_t *, uint32_t, uint8_t *, int, wvb_block_result *);
+typedef void (*pcm_kernel_t)(const uint8_t *, const wvb_block_desc *, const uint32_t *, uint32_t, uint8_t *, int, wvb_block_result *, uint32_t);
 
 // the one-warp-CTA builds of the generic kernels (large shared-memory classes)
 pcm_kernel_t pcm_kernel_small(int variant)
@@ -175,7 +177,7 @@ pcm_kernel_t pcm_kernel_small(int variant)
     }
 }
 
-pcm_kernel_t pcm_kernel(int variant, uint32_t count = 0, int sm_count = 148)
+pcm_kernel_t pcm_kernel(int variant)
 {
     switch (variant) {
     case wvb::V_MONO: return k_decode_pcm<false, false, false, GenM>;
@@ -183,20 +185,13 @@ pcm_kernel_t pcm_kernel(int variant, uint32_t count = 0, int sm_count = 148)
     case wvb::V_STEREO | wvb::V_F16: return k_decode_pcm<true, false, false, GenS, 0, true>;
     case wvb::V_MONO | wvb::V_FIXED: return k_decode_pcm<false, false, false, FixM>;
     case wvb::V_STEREO | wvb::V_FIXED: return k_decode_pcm<true, false, false, FixS>;
-    case wvb::V_STEREO | wvb::V_FIXED | wvb::V_F16: {
-        // Two builds of the same kernel: 90 registers (5 CTAs/SM, no spills) and, compiled for 6 resident CTAs/SM, 80 registers
-        // with ~40 B of spills.  The second wins once the launch no longer fits one wave of the first (measured on B200 at
-        // 200k blocks: 92.9 vs 86.9 ms; capping further to 72 / 64 registers costs more in spills than occupancy returns:
-        // 120 / 124 ms).  WVB_FIXED_OCC=0|6 overrides for experiments.
-        static const int env_occ = getenv("WVB_FIXED_OCC") ? atoi(getenv("WVB_FIXED_OCC")) : -1;
-        const int occ = env_occ >= 0 ? env_occ : (count > (uint32_t)sm_count * 5u * CTA_THREADS ? 6 : 0);
-        if (occ == 6) return k_decode_pcm<true, false, false, FixS, 6, true>;
-        return k_decode_pcm<true, false, false, FixS, 0, true>;
-    }
+    // (Round 1 also shipped builds of the two five-term kernels capped at 80 registers, 6 CTAs per SM with ~40 B of spills, and
+    // used them for launches of more than one wave.  With the round-2 decoder the uncapped build -- 88 registers, 5 CTAs, no
+    // spills -- wins at every size: 75.7 vs 76.6 ms at 200k blocks, 50.5 vs 54.4 ms at 120k; with the staged output the
+    // capped build spills the flush: 77.0 vs 78.8 ms.  The capped builds are gone.)
+    case wvb::V_STEREO | wvb::V_FIXED | wvb::V_F16: return k_decode_pcm<true, false, false, FixS, 0, true>;
     case wvb::V_STEREO | wvb::V_FIXED_B: return k_decode_pcm<true, false, false, FixSB>;
-    case wvb::V_STEREO | wvb::V_FIXED_B | wvb::V_F16:
-        if (count > (uint32_t)sm_count * 5u * CTA_THREADS) return k_decode_pcm<true, false, false, FixSB, 6, true>;
-        return k_decode_pcm<true, false, false, FixSB, 0, true>;
+    case wvb::V_STEREO | wvb::V_FIXED_B | wvb::V_F16: return k_decode_pcm<true, false, false, FixSB, 0, true>;
     case wvb::V_STEREO | wvb::V_FIXED_C: return k_decode_pcm<true, false, false, FixSC>;
     case wvb::V_STEREO | wvb::V_FIXED_C | wvb::V_F16: return k_decode_pcm<true, false, false, FixSC, 0, true>;
     case wvb::V_MONO | wvb::V_GENFIX: return k_decode_pcm<false, false, true, GenM>;
@@ -205,6 +200,21 @@ pcm_kernel_t pcm_kernel(int variant, uint32_t count = 0, int sm_count = 148)
     case wvb::V_STEREO | wvb::V_GENFIX | wvb::V_HYBRID: return k_decode_pcm<true, true, true, GenS>;
     default: return nullptr;
     }
+}
+
+// Small launches.  A block is a serial chain, so a launch of a few hundred blocks (BASELINE configs[0]: one 60 s file, 120
+// blocks) cannot use the machine whatever the mapping, and its duration is the latency of one chain: 17.6 ms for a 22 050-
+// sample stereo block, the same from 320 to 18 000 blocks per launch (measured, round 2).  Packed 32 to a warp every lane
+// pays for every branch direction any of the 32 takes; alone in its warp a lane executes its own path only.  That is worth
+// 10 % (15.96 ms at 320 blocks) -- the chain is bound by the dependent-issue latency of its ~300 instructions per frame, not
+// by divergence -- and only while every block can have a scheduler to itself: with 2 to 16 blocks per warp over more warps
+// the same launches got 3-9 % slower (2000 / 10 000 / 18 000 blocks: 19.5 / 20.8 / 21.1 vs 18.8 / 19.4 / 19.4 ms).
+// So: one lane per warp (spread = 5) up to one block per scheduler, packed warps otherwise.
+uint32_t pick_spread(uint32_t count, int sm_count)
+{
+    static const int env = getenv("WVB_SPREAD") ? atoi(getenv("WVB_SPREAD")) : -1; // experiments: force an exponent
+    if (env >= 0) return (uint32_t)std::min(env, 5);
+    return count <= (uint32_t)sm_count * 4u ? 5u : 0u;
 }
 
 // shared-memory size classes (words per thread); a launch uses the smallest class that fits its blocks
@@ -462,7 +472,7 @@ static int launch_plan(wvb_batch *b, const std::vector<Launch> &plan, const uint
                 return set_error(rc, std::string("DSD launch failed (unsupported dsd mode or CUDA error): ") + cudaGetErrorString(cudaGetLastError()));
             continue;
         }
-        pcm_kernel_t k = pcm_kernel(L.variant, L.count, b->sm_count);
+        pcm_kernel_t k = pcm_kernel(L.variant);
         int cta = CTA_THREADS;
         if (L.cls > SMEM_CLASS_SMALL_CTA) {
             pcm_kernel_t ks = pcm_kernel_small(L.variant);
@@ -474,8 +484,9 @@ static int launch_plan(wvb_batch *b, const std::vector<Launch> &plan, const uint
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // (left alone, the driver sizes the shared-memory carve-out for fewer CTAs than the state allows)
         if (cta == CTA_SMALL) CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        unsigned grid = (L.count + cta - 1) / cta;
-        k<<<grid, cta, smem, s>>>(din, b->d_descs, b->d_order + L.first, L.count, dout, fmt == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : fmt, dres);
+        const uint32_t spread = pick_spread(L.count, b->sm_count);
+        unsigned grid = (unsigned)((((uint64_t)L.count << spread) + cta - 1) / cta);
+        k<<<grid, cta, smem, s>>>(din, b->d_descs, b->d_order + L.first, L.count, dout, fmt == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : fmt, dres, spread);
         CUDA_TRY(cudaGetLastError());
         b->launches++;
     }
