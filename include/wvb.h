@@ -290,6 +290,20 @@ int wvb_stored_md5(const uint8_t *file, size_t len, uint8_t md5[16]);
  * WVB_RF_BLOCK_CHECKSUM. */
 int wvb_block_checksum_ok(const uint8_t *block, size_t len);
 
+/* Index AND decode a slab of files in one call (host input, host or device output).  Same results as wvb_index_many followed
+ * by wvb_batch_decode -- the same table layout (first / count / file_out_offset, descriptors rebased for a file-major
+ * output slab with every file 16-byte aligned), the same output bytes and block results -- but the index pass overlaps the
+ * upload and decode: files are indexed in slab order by `threads` host threads while the segments whose files are already
+ * indexed are uploaded, decoded and downloaded.  offsets[] must be ascending and the files disjoint.  `blocks` (cap
+ * entries) receives the table, `out` (out_cap bytes) the samples.  If cap or out_cap is too small the contents of `out` are
+ * unspecified, *nblocks / *out_bytes hold the sizes needed and the call returns WVB_E_CAPACITY (callers that decode similar
+ * batches repeatedly keep the previous sizes).  mem_flags: WVB_OUT_DEVICE and WVB_NO_SYNC only.
+ * Replaces the open / unpack loop of WvDemo.cs:41-141 run over many files. */
+int wvb_batch_decode_files(wvb_batch *b, const uint8_t *slab, size_t slab_bytes, const uint64_t *offsets, const uint64_t *sizes, size_t nfiles,
+                           uint32_t open_flags, uint32_t chunk_samples, int out_format, int threads, wvb_file_info *infos,
+                           wvb_block_desc *blocks, size_t cap, uint64_t *first, uint64_t *count, uint64_t *file_out_offset, size_t *nblocks,
+                           uint64_t *out_bytes, void *out, size_t out_cap, uint32_t mem_flags, wvb_block_result *results);
+
 /* pinned host memory helpers for hosts without their own allocator (C# shim) */
 void *wvb_host_alloc(size_t bytes);
 void wvb_host_free(void *p);

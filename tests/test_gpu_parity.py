@@ -282,3 +282,43 @@ def test_staged_16bit_stereo_output_writes_only_its_own_bytes(gpu, terms):
             assert np.array_equal(got[lo:lo + want.size], want), i
         untouched[lo:lo + want.size] = False
     assert (got[untouched] == 0xEE).all()
+
+
+def test_decode_slab_overlapped_index_matches_the_two_call_path(gpu):
+    """wvb_batch_decode_files (index pass overlapped with upload and decode) returns the same table, output bytes and
+    block results as wvb_index_many + wvb_batch_decode, for a mixed slab including a damaged file, an unopenable one,
+    DSD (whose scratch tables are sized on the way) and enough files for several segments' worth of launches."""
+    from wavpackdecoder_b200.batch import BatchDecoder, Corpus, WvbError
+    kinds = [dict(), dict(bits=24), dict(channels=1), dict(kind=1), dict(bits=32, int32_sent_bits=8), dict(kind=3, dsd_mode=1, block_samples=4000),
+             dict(kind=3, dsd_mode=3, block_samples=4000), dict(terms=[18, 2, 18, 3, -2], deltas=[2] * 5), dict(bits=8)]
+    files = []
+    for k in range(90):
+        kw = dict(kinds[k % len(kinds)])
+        secs = 0.02 if kw.get("kind") == 3 else 0.05 + 0.01 * (k % 7)
+        files.append(bytearray(make_file(seed=0xD00 + k, seconds=secs, **kw)[2]))
+    files[13][len(files[13]) // 2] ^= 0x20
+    files[40][0:4] = b"nope"
+    two = Corpus.from_files([bytes(f) for f in files], out_format=gpu.OUT_PCM)
+    dec = BatchDecoder(0)
+    try:
+        want, want_res = dec.decode_corpus(two)
+        out = np.full(two.out_bytes + 64, 0xEE, dtype=np.uint8)
+        one, res = dec.decode_slab(two.slab, two.offsets, two.sizes, out, cap_hint=two.nblocks + 7, out_format=gpu.OUT_PCM, threads=4)
+        assert one.nblocks == two.nblocks and one.out_bytes == two.out_bytes
+        assert np.array_equal(one.first, two.first) and np.array_equal(one.count, two.count) and np.array_equal(one.file_out_offset, two.file_out_offset)
+        assert bytes(one._descs_mem[:two.nblocks * C.sizeof(gpu.BlockDesc)]) == bytes(two._descs_mem[:two.nblocks * C.sizeof(gpu.BlockDesc)])
+        for i in range(two.nfiles):
+            assert np.array_equal(one.file_output(out, i), two.file_output(want, i)), i
+            assert one.infos[i].status == two.infos[i].status and one.infos[i].indexed_samples == two.infos[i].indexed_samples
+        for k in range(two.nblocks):
+            assert (res[k].crc, res[k].rflags, res[k].mute_from, res[k].crc_x) == (want_res[k].crc, want_res[k].rflags, want_res[k].mute_from, want_res[k].crc_x), k
+        # too small a table / output: nothing decoded, the sizes needed come back
+        for cap, ocap in ((two.nblocks - 1, out.size), (two.nblocks, two.out_bytes - 17)):  # (out_bytes ends with up to 15 bytes of padding)
+            with pytest.raises(WvbError) as e:
+                dec.decode_slab(two.slab, two.offsets, two.sizes, out, cap_hint=cap, out_format=gpu.OUT_PCM, out_cap=ocap)
+            assert e.value.needed == (two.nblocks, two.out_bytes)
+        # files out of slab order are refused
+        with pytest.raises(WvbError):
+            dec.decode_slab(two.slab, two.offsets[::-1].copy(), two.sizes[::-1].copy(), out, cap_hint=two.nblocks, out_format=gpu.OUT_PCM)
+    finally:
+        dec.close()

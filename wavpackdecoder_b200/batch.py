@@ -26,7 +26,7 @@ class Corpus:
     slab: uint8 numpy array (ideally pinned), offsets/sizes: per-file byte ranges.
     """
 
-    def __init__(self, slab, offsets, sizes, open_flags=0, chunk_samples=4096, out_format=N.OUT_PCM, threads=0, cap_hint=0):
+    def __init__(self, slab, offsets, sizes, open_flags=0, chunk_samples=4096, out_format=N.OUT_PCM, threads=0, cap_hint=0, index=True):
         lib = N.load()
         self.lib = lib
         self.slab = slab
@@ -35,10 +35,15 @@ class Corpus:
         self.nfiles = int(self.offsets.size)
         self.out_format = out_format
         self.open_flags = open_flags
+        self.chunk_samples = chunk_samples
         self.infos = (N.FileInfo * max(self.nfiles, 1))()
         self.first = np.zeros(self.nfiles, dtype=np.uint64)
         self.count = np.zeros(self.nfiles, dtype=np.uint64)
         self.file_out_offset = np.zeros(self.nfiles, dtype=np.uint64)
+        self.nblocks = 0
+        self.out_bytes = 0
+        if not index:  # BatchDecoder.decode_slab fills the table while it decodes
+            return
         nblocks = C.c_size_t()
         out_bytes = C.c_uint64()
         args = (slab.ctypes.data, self.offsets.ctypes.data, self.sizes.ctypes.data, self.nfiles, open_flags, chunk_samples,
@@ -142,6 +147,33 @@ class BatchDecoder:
         rc = self.lib.wvb_batch_md5(self.h, device_out, out_bytes, offs.ctypes.data, lens.ctypes.data, offs.size, dig.ctypes.data)
         _check(self.lib, rc, "wvb_batch_md5")
         return dig
+
+    def decode_slab(self, slab, offsets, sizes, out, cap_hint, open_flags=0, chunk_samples=4096, out_format=N.OUT_PCM, threads=0,
+                    mem_flags=0, out_ptr=None, out_cap=None):
+        """Index and decode a host slab of files in ONE library call (wvb_batch_decode_files): the index pass overlaps the
+        upload and decode of the files already indexed.  offsets must ascend.  `out`: a uint8 numpy array (or, with
+        N.OUT_DEVICE in mem_flags, pass out_ptr / out_cap of a device buffer).  cap_hint: block-table capacity (the block
+        count of a previous, similar batch; a table or output that turns out too small raises WvbError with the sizes needed
+        in .needed).  Returns (Corpus with the table filled in, results array)."""
+        corpus = Corpus(slab, offsets, sizes, open_flags=open_flags, chunk_samples=chunk_samples, out_format=out_format, index=False)
+        cap = max(int(cap_hint), 1)
+        corpus._descs_mem = np.empty(cap * C.sizeof(N.BlockDesc), dtype=np.uint8)
+        corpus.descs = (N.BlockDesc * cap).from_buffer(corpus._descs_mem)
+        results = (N.BlockResult * cap)()
+        nblocks, out_bytes = C.c_size_t(), C.c_uint64()
+        optr = out.ctypes.data if out_ptr is None else out_ptr
+        ocap = int(out.size) if out_cap is None else int(out_cap)
+        rc = self.lib.wvb_batch_decode_files(self.h, slab.ctypes.data, slab.size, corpus.offsets.ctypes.data, corpus.sizes.ctypes.data, corpus.nfiles,
+                                             open_flags, chunk_samples, out_format, threads, corpus.infos, corpus.descs, cap,
+                                             corpus.first.ctypes.data, corpus.count.ctypes.data, corpus.file_out_offset.ctypes.data,
+                                             C.byref(nblocks), C.byref(out_bytes), optr, ocap, mem_flags, C.addressof(results))
+        corpus.nblocks, corpus.out_bytes = int(nblocks.value), int(out_bytes.value)
+        if rc == N.E_CAPACITY:
+            e = WvbError("wvb_batch_decode_files: table or output too small (need %d blocks, %d bytes)" % (corpus.nblocks, corpus.out_bytes))
+            e.needed = (corpus.nblocks, corpus.out_bytes)
+            raise e
+        _check(self.lib, rc, "wvb_batch_decode_files")
+        return corpus, results
 
     def decode_corpus(self, corpus, out=None):
         """Host-buffer decode of a whole Corpus.  Returns (out uint8 array, results array)."""

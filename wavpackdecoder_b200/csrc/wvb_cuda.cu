@@ -9,6 +9,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <memory>
+#include <thread>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -119,6 +122,7 @@ struct wvb_batch {
     // pinned staging of the small per-call arrays: copies from / into pageable memory are staged by the driver and block the
     // host thread on the stream they are queued on
     uint32_t *h_order = nullptr; size_t h_order_cap = 0;
+    wvb_block_desc *h_descs = nullptr; size_t h_descs_cap = 0; // table slices of wvb_batch_decode_files
     wvb_block_result *h_results = nullptr; size_t h_results_cap = 0;
     wvb_block_result *pending_results = nullptr; size_t pending_n = 0; bool pending_copy = false;
     // WVB_TRACE=1: per-segment timeline of the pipelined host-buffer decode, printed by wvb_batch_wait
@@ -316,6 +320,7 @@ void wvb_batch_destroy(wvb_batch *b)
     cudaFree(b->d_in); cudaFree(b->d_out); cudaFree(b->d_descs); cudaFree(b->d_order); cudaFree(b->d_results);
     cudaFree(b->d_scratch); cudaFree(b->d_scratch_meta);
     if (b->h_order) cudaFreeHost(b->h_order);
+    if (b->h_descs) cudaFreeHost(b->h_descs);
     if (b->h_results) cudaFreeHost(b->h_results);
     for (auto &t : b->trace) { cudaEventDestroy(t.up); cudaEventDestroy(t.dec); cudaEventDestroy(t.down); }
     if (b->trace_t0) cudaEventDestroy(b->trace_t0);
@@ -761,6 +766,231 @@ int wvb_batch_decode(wvb_batch *b, const uint8_t *in, size_t in_bytes, const wvb
         if (nblocks) CUDA_TRY(cudaMemcpyAsync(b->h_results, dres, nblocks * sizeof(wvb_block_result), cudaMemcpyDeviceToHost, s));
         b->pending_results = results;
         b->pending_n = nblocks;
+        b->pending_copy = true;
+    }
+    CUDA_TRY(cudaEventRecord(b->ev[3], s));
+    b->timed = true;
+    if (!(mem_flags & WVB_NO_SYNC)) return wvb_batch_wait(b);
+    return WVB_OK;
+}
+
+// Index + decode in one call, for host slabs: the index pass (host threads, file by file in slab order) runs WHILE the first
+// segments are uploaded and decoded.  wvb_index_many + wvb_batch_decode put the whole index pass (20-25 ms for 10 000 files)
+// in front of the first upload; here the first kernel launch waits for the files of the first, small segment only, and
+// every later segment is launched as soon as the contiguous prefix of indexed files covers it.
+int wvb_batch_decode_files(wvb_batch *b, const uint8_t *slab, size_t slab_bytes, const uint64_t *offsets, const uint64_t *sizes, size_t nfiles,
+                           uint32_t open_flags, uint32_t chunk_samples, int out_format, int threads, wvb_file_info *infos,
+                           wvb_block_desc *blocks, size_t cap, uint64_t *first, uint64_t *count, uint64_t *file_out_offset, size_t *nblocks,
+                           uint64_t *out_bytes, void *out, size_t out_cap, uint32_t mem_flags, wvb_block_result *results)
+{
+    if (!b || !slab || !offsets || !sizes || !infos || !blocks || !first || !count || !file_out_offset || !out) return WVB_E_ARG;
+    if (out_format != WVB_OUT_INT32 && out_format != WVB_OUT_PCM && out_format != WVB_OUT_DSD_RAW) return WVB_E_ARG;
+    if (mem_flags & ~(uint32_t)(WVB_OUT_DEVICE | WVB_NO_SYNC)) return set_error(WVB_E_ARG, "wvb_batch_decode_files takes host input and host results");
+    if (cap > 0xfffffff0ull) return WVB_E_ARG;
+    for (size_t i = 0; i < nfiles; i++) {
+        if (sizes[i] > slab_bytes || offsets[i] > slab_bytes - sizes[i]) return set_error(WVB_E_ARG, "file outside the slab");
+        if (i && offsets[i] < offsets[i - 1] + sizes[i - 1]) return set_error(WVB_E_ARG, "files must be in slab order and disjoint");
+    }
+    CUDA_TRY(cudaSetDevice(b->device));
+    const bool out_device = (mem_flags & WVB_OUT_DEVICE) != 0;
+    const int ofmt = out_format == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : out_format;
+    cudaStream_t s = b->stream;
+    b->timed = false;
+    b->launches = 0;
+    b->prepared = false;
+    b->plan.clear();
+    int rc;
+
+    // segments by input bytes (the output size is not known yet), sizes ramping 1,2,3,4,...,4,3,2,1 as in decode_pipelined
+    size_t nseg = (size_t)std::min<uint64_t>(16, std::max<uint64_t>(1, (uint64_t)slab_bytes * 3 / ((uint64_t)1536 << 20)));
+    if (nfiles < 64) nseg = 1;
+    std::vector<uint64_t> quota(nseg);
+    {
+        uint64_t wsum = 0, in_total = 0;
+        for (size_t i = 0; i < nfiles; i++) in_total += sizes[i];
+        std::vector<uint64_t> wt(nseg);
+        for (size_t k = 0; k < nseg; k++) { wt[k] = std::min<uint64_t>(std::min<uint64_t>(k + 1, nseg - k), 4); wsum += wt[k]; }
+        for (size_t k = 0; k < nseg; k++) quota[k] = in_total / wsum * wt[k] + 1;
+    }
+    if (!b->s_in) CUDA_TRY(cudaStreamCreateWithFlags(&b->s_in, cudaStreamNonBlocking));
+    if (!b->s_out) CUDA_TRY(cudaStreamCreateWithFlags(&b->s_out, cudaStreamNonBlocking));
+    while (b->seg_streams.size() < nseg + 1) {
+        cudaStream_t st;
+        CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        b->seg_streams.push_back(st);
+    }
+    while (b->seg_ev.size() < 2 * (nseg + 1) + 2) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        b->seg_ev.push_back(e);
+    }
+    if ((rc = ensure(b->d_in, b->d_in_cap, slab_bytes + 64)) != WVB_OK) return rc;
+    if (!out_device && (rc = ensure(b->d_out, b->d_out_cap, out_cap + 64)) != WVB_OK) return rc;
+    uint8_t *dout = out_device ? (uint8_t *)out : b->d_out;
+    if ((rc = ensure(b->d_results, b->d_results_cap, cap + 1)) != WVB_OK) return rc;
+    if ((rc = ensure(b->d_descs, b->d_descs_cap, cap + 1)) != WVB_OK) return rc;
+    if ((rc = ensure(b->d_order, b->d_order_cap, cap + 1)) != WVB_OK) return rc;
+    if ((rc = ensure_pinned(b->h_order, b->h_order_cap, cap + 1)) != WVB_OK) return rc;
+    if ((rc = ensure_pinned(b->h_descs, b->h_descs_cap, cap + 1)) != WVB_OK) return rc;
+    static const bool tracing = getenv("WVB_TRACE") && atoi(getenv("WVB_TRACE"));
+    const auto host_t0 = std::chrono::steady_clock::now();
+    auto host_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
+    for (auto &t : b->trace) { cudaEventDestroy(t.up); cudaEventDestroy(t.dec); cudaEventDestroy(t.down); }
+    b->trace.clear();
+    if (tracing) {
+        if (!b->trace_t0) CUDA_TRY(cudaEventCreate(&b->trace_t0));
+        CUDA_TRY(cudaEventRecord(b->trace_t0, s));
+    }
+    CUDA_TRY(cudaEventRecord(b->ev[0], s));
+    CUDA_TRY(cudaEventRecord(b->ev[1], s));
+    CUDA_TRY(cudaEventRecord(b->seg_ev[2 * (nseg + 1)], s));
+    CUDA_TRY(cudaStreamWaitEvent(b->s_in, b->seg_ev[2 * (nseg + 1)], 0)); // (work queued on the batch's stream before this call)
+
+    // ---- index workers: files are handed out in order, each file's descriptors land in a block of its own ----
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    threads = (int)std::min<size_t>((size_t)threads, std::max<size_t>(nfiles, 1));
+    std::vector<std::vector<wvb_block_desc>> per_file(nfiles);
+    std::unique_ptr<std::atomic<uint8_t>[]> done(new std::atomic<uint8_t>[nfiles ? nfiles : 1]);
+    for (size_t i = 0; i < nfiles; i++) done[i].store(0, std::memory_order_relaxed);
+    std::atomic<size_t> next{0};
+    std::atomic<bool> cancel{false};
+    auto walk = [&]() {
+        std::vector<wvb_block_desc> scratch(256);
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= nfiles) break;
+            size_t n = 0;
+            if (!cancel.load(std::memory_order_relaxed)) {
+                for (;;) {
+                    const int r = wvb_index(slab + offsets[i], (size_t)sizes[i], open_flags, chunk_samples, &infos[i], scratch.data(), scratch.size(), &n);
+                    if (r != WVB_E_CAPACITY) break;
+                    scratch.resize(n + n / 4 + 16);
+                }
+                per_file[i].assign(scratch.begin(), scratch.begin() + (ptrdiff_t)n);
+            }
+            count[i] = n;
+            done[i].store(1, std::memory_order_release);
+        }
+    };
+    std::vector<std::thread> workers;
+    for (int t = 0; t < threads; t++) workers.emplace_back(walk);
+    auto finish_workers = [&]() { for (auto &t : workers) if (t.joinable()) t.join(); };
+    auto drain = [&]() {
+        if (b->s_in) cudaStreamSynchronize(b->s_in);
+        for (cudaStream_t st : b->seg_streams) cudaStreamSynchronize(st);
+        if (b->s_out) cudaStreamSynchronize(b->s_out);
+        cudaStreamSynchronize(b->stream);
+    };
+    auto fail = [&](int code) {
+        const std::string msg = g_last_error;
+        cancel.store(true);
+        finish_workers();
+        drain();
+        cudaGetLastError();
+        b->pending_copy = false;
+        g_last_error = msg;
+        return code;
+    };
+
+    // ---- the main thread follows the contiguous prefix of indexed files, lays the table out and launches segments ----
+    uint64_t total = 0, obytes = 0, seg_acc = 0;
+    size_t seg_k = 0, seg_first_block = 0, seg_first_file = 0;
+    bool too_small = false;
+    std::vector<uint32_t> tmp_order;
+    std::vector<Launch> plan;
+    for (size_t i = 0; i < nfiles; i++) {
+        while (!done[i].load(std::memory_order_acquire)) std::this_thread::yield();
+        const size_t n = (size_t)count[i];
+        first[i] = total;
+        file_out_offset[i] = obytes;
+        const uint32_t unit = out_format == WVB_OUT_INT32 ? 4u : (uint32_t)infos[i].bytes_per_sample;
+        const uint32_t ch = (open_flags & WVB_OPEN_ALL_CHANNELS) ? (uint32_t)infos[i].num_channels
+                                                                 : (uint32_t)(infos[i].reduced_channels > 0 ? infos[i].reduced_channels : infos[i].num_channels);
+        const uint64_t fbytes = (uint64_t)infos[i].indexed_samples * unit * ch;
+        if (total + n > cap || obytes + fbytes > out_cap) too_small = true; // keep counting: the caller gets the sizes needed
+        if (!too_small && n) {
+            memcpy(blocks + total, per_file[i].data(), n * sizeof(wvb_block_desc));
+            wvb_rebase(blocks + total, n, offsets[i], obytes, out_format, (uint32_t)i);
+        }
+        std::vector<wvb_block_desc>().swap(per_file[i]);
+        total += n;
+        obytes = (obytes + fbytes + 15) & ~(uint64_t)15;
+        seg_acc += sizes[i];
+        const bool last = i + 1 == nfiles;
+        if (too_small || !(seg_acc >= quota[std::min(seg_k, nseg - 1)] || last)) continue;
+        // launch segment seg_k: files [seg_first_file, i], blocks [seg_first_block, total)
+        const size_t bfirst = seg_first_block, bcount = (size_t)total - seg_first_block;
+        const uint64_t in_lo = offsets[seg_first_file], in_hi = offsets[i] + sizes[i];
+        const uint64_t out_lo = file_out_offset[seg_first_file], out_hi = std::min<uint64_t>(obytes, out_cap);
+        seg_first_block = (size_t)total;
+        seg_first_file = i + 1;
+        seg_acc = 0;
+        const size_t k = std::min(seg_k, nseg);
+        seg_k++;
+        if (!bcount) continue;
+        if ((rc = validate_table(blocks + bfirst, bcount, slab_bytes, out_cap, out_format)) != WVB_OK) return fail(rc);
+        make_plan(blocks + bfirst, bcount, out_format, tmp_order, plan);
+        for (size_t j = 0; j < bcount; j++) b->h_order[bfirst + j] = (uint32_t)(tmp_order[j] + bfirst);
+        for (Launch &L : plan) L.first += (uint32_t)bfirst;
+        { // DSD fast-mode tables: the scratch may only grow while nothing runs
+            size_t slots = 0;
+            for (const Launch &L : plan)
+                if (L.variant == wvb::V_DSD && L.cls >= 16) slots = std::max(slots, (size_t)L.first + L.count);
+            if (slots * wvb::DSD_FAST_TABLE_STRIDE > b->d_scratch_cap || slots * sizeof(wvb::DsdFastMeta) > b->d_scratch_meta_cap) {
+                drain();
+                if ((rc = ensure(b->d_scratch, b->d_scratch_cap, std::max<size_t>(slots, cap) * wvb::DSD_FAST_TABLE_STRIDE)) != WVB_OK) return fail(rc);
+                if ((rc = ensure(b->d_scratch_meta, b->d_scratch_meta_cap, std::max<size_t>(slots, cap) * sizeof(wvb::DsdFastMeta))) != WVB_OK) return fail(rc);
+            }
+        }
+        memcpy(b->h_descs + bfirst, blocks + bfirst, bcount * sizeof(wvb_block_desc));
+        cudaStream_t ks = b->seg_streams[k];
+        auto cu = [&](cudaError_t e, const char *what) -> int {
+            if (e == cudaSuccess) return WVB_OK;
+            return set_error(WVB_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+        };
+        if ((rc = cu(cudaMemcpyAsync(b->d_descs + bfirst, b->h_descs + bfirst, bcount * sizeof(wvb_block_desc), cudaMemcpyHostToDevice, b->s_in), "descs upload")) != WVB_OK) return fail(rc);
+        if ((rc = cu(cudaMemcpyAsync(b->d_order + bfirst, b->h_order + bfirst, bcount * sizeof(uint32_t), cudaMemcpyHostToDevice, b->s_in), "order upload")) != WVB_OK) return fail(rc);
+        if ((rc = cu(cudaMemcpyAsync(b->d_in + in_lo, slab + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, b->s_in), "slab upload")) != WVB_OK) return fail(rc);
+        if ((rc = cu(cudaEventRecord(b->seg_ev[2 * k], b->s_in), "event")) != WVB_OK) return fail(rc);
+        wvb_batch::TraceSeg tr{nullptr, nullptr, nullptr, bcount, in_hi - in_lo, out_hi - out_lo, 0};
+        if (tracing) {
+            cudaEventCreate(&tr.up); cudaEventCreate(&tr.dec); cudaEventCreate(&tr.down);
+            cudaEventRecord(tr.up, b->s_in);
+        }
+        if ((rc = cu(cudaStreamWaitEvent(ks, b->seg_ev[2 * k], 0), "wait")) != WVB_OK) return fail(rc);
+        if ((rc = launch_plan(b, plan, b->d_in, dout, out_format, b->d_results, ks)) != WVB_OK) return fail(rc);
+        if ((rc = cu(cudaEventRecord(b->seg_ev[2 * k + 1], ks), "event")) != WVB_OK) return fail(rc);
+        cudaStreamWaitEvent(b->s_out, b->seg_ev[2 * k + 1], 0);
+        cudaStreamWaitEvent(s, b->seg_ev[2 * k + 1], 0);
+        if (!out_device && out_hi > out_lo &&
+            (rc = cu(cudaMemcpyAsync((uint8_t *)out + out_lo, dout + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, b->s_out), "download")) != WVB_OK)
+            return fail(rc);
+        if (tracing) {
+            cudaEventRecord(tr.dec, ks);
+            cudaEventRecord(tr.down, b->s_out);
+            tr.host_ms = host_ms();
+            b->trace.push_back(tr);
+        }
+        (void)ofmt;
+    }
+    finish_workers();
+    b->trace_host_total_ms = host_ms();
+    if (nblocks) *nblocks = (size_t)total;
+    if (out_bytes) *out_bytes = obytes;
+    if (too_small) {
+        drain();
+        b->pending_copy = false;
+        return set_error(WVB_E_CAPACITY, "block table or output slab too small: *nblocks / *out_bytes hold the sizes needed");
+    }
+    CUDA_TRY(cudaEventRecord(b->ev[2], s));
+    CUDA_TRY(cudaEventRecord(b->seg_ev[2 * (nseg + 1) + 1], b->s_out));
+    CUDA_TRY(cudaStreamWaitEvent(s, b->seg_ev[2 * (nseg + 1) + 1], 0));
+    b->pending_copy = false;
+    if (results && total) {
+        if ((rc = ensure_pinned(b->h_results, b->h_results_cap, (size_t)total + 1)) != WVB_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(b->h_results, b->d_results, (size_t)total * sizeof(wvb_block_result), cudaMemcpyDeviceToHost, s));
+        b->pending_results = results;
+        b->pending_n = (size_t)total;
         b->pending_copy = true;
     }
     CUDA_TRY(cudaEventRecord(b->ev[3], s));
