@@ -91,6 +91,11 @@ namespace WavPack
         [DllImport(Lib)] internal static extern void wvb_batch_destroy(IntPtr batch);
         [DllImport(Lib)] internal static extern unsafe int wvb_batch_decode(IntPtr batch, byte* input, UIntPtr in_bytes, BlockDesc* descs, UIntPtr nblocks,
             void* output, UIntPtr out_bytes, int out_format, uint mem_flags, BlockResult* results);
+        // index + decode of a slab of files in one call: the index pass overlaps the upload / decode / download (batch hosts)
+        [DllImport(Lib)] internal static extern unsafe int wvb_batch_decode_files(IntPtr batch, byte* slab, UIntPtr slab_bytes, ulong* offsets, ulong* sizes,
+            UIntPtr nfiles, uint open_flags, uint chunk_samples, int out_format, int threads, FileInfo* infos, BlockDesc* blocks, UIntPtr cap,
+            ulong* first, ulong* count, ulong* file_out_offset, UIntPtr* nblocks, ulong* out_bytes, void* output, UIntPtr out_cap, uint mem_flags,
+            BlockResult* results);
         [DllImport(Lib)] internal static extern IntPtr wvb_host_alloc(UIntPtr bytes); // pinned host memory
         [DllImport(Lib)] internal static extern void wvb_host_free(IntPtr p);
         // integrity (beyond the reference, which ignores ID_MD5_CHECKSUM): MD5 of decoded ranges on the device, stored digest lookup

@@ -75,6 +75,17 @@ def test_dff_header_round_trip():
         assert ds == len(data) and blob[do:do + ds] == data
 
 
+def test_caf_header_round_trip():
+    from wavpackdecoder_b200 import containers as K
+    for n, ch, rate, bits, byteps in [(1000, 2, 44100, 16, 2), (77, 1, 96000, 24, 3), (0, 6, 48000, 32, 4)]:
+        h = K.caf_header(n, ch, rate, bits, byteps)
+        assert len(h) == 68 and h[:4] == b"caff" and struct.unpack_from(">HH", h, 4) == (1, 0)
+        assert h[8:12] == b"desc" and struct.unpack_from(">q", h, 12)[0] == 32
+        sr, fid, flags, bpp, fpp, cpf, bpc = struct.unpack_from(">d4sIIIII", h, 20)
+        assert (sr, fid, flags, bpp, fpp, cpf, bpc) == (float(rate), b"lpcm", 2, byteps * ch, 1, ch, bits)
+        assert h[52:56] == b"data" and struct.unpack_from(">qI", h, 56) == (4 + n * ch * byteps, 0)
+
+
 def _with_file_format(data, fmt):
     """Set the file_format byte of the ID_NEW_CONFIG_BLOCK the synthetic encoder writes (one payload byte, odd-size flag)."""
     data = bytearray(data)
@@ -92,12 +103,13 @@ def test_native_containers_on_device():
     pcm24 = _with_file_format(make_file(extras=X_CONFIG | X_NEW_CONFIG, bits=24, channels=1, nsamples=10001)[2], K.WP_FORMAT_W64)
     wav = bytes(make_file(extras=X_CONFIG | X_NEW_CONFIG, seconds=0.3)[2])
     stored = bytes(make_file(extras=X_RIFF | X_CONFIG, seconds=0.3)[2])
+    caf = _with_file_format(make_file(extras=X_CONFIG | X_NEW_CONFIG, bits=24, seconds=0.2)[2], K.WP_FORMAT_CAF)
     dsd = _with_file_format(make_file(kind=KIND_DSD, dsd_mode=1, extras=X_CONFIG | X_NEW_CONFIG, seconds=0.05, block_samples=4000)[2], K.WP_FORMAT_DFF)
     dsd_mono = _with_file_format(make_file(kind=KIND_DSD, dsd_mode=3, channels=1, extras=X_CONFIG | X_NEW_CONFIG, nsamples=4097, block_samples=2000)[2], K.WP_FORMAT_DFF)
-    files = [pcm16, pcm24, wav, stored, dsd, dsd_mono]
+    files = [pcm16, pcm24, wav, stored, dsd, dsd_mono, caf]
     res = unpack_files(files, container="native")
     assert [code for _b, code in res] == [0] * len(files)
-    for data, (blob, _code), kind in zip(files, res, ["w64", "w64", "wav", "stored", "dff", "dff"]):
+    for data, (blob, _code), kind in zip(files, res, ["w64", "w64", "wav", "stored", "dff", "dff", "caf"]):
         ref, errs, status, info = oracle_decode(data)
         assert status == 0 and errs == 0
         if kind == "w64":
@@ -105,6 +117,9 @@ def test_native_containers_on_device():
             do, dl = chunks["data"]
             assert blob[do:do + dl] == format_samples(ref, info["bytes_per_sample"]).tobytes()
             assert struct.unpack_from("<HHI", blob, chunks["fmt "][0]) == (1, info["reduced_channels"], info["sample_rate"])
+        elif kind == "caf":
+            assert blob[:4] == b"caff" and blob[68:] == format_samples(ref, info["bytes_per_sample"]).tobytes()
+            assert struct.unpack_from(">q", blob, 56)[0] == 4 + len(blob) - 68
         elif kind in ("wav", "stored"):
             assert blob[:4] == b"RIFF" and blob[44:] == format_samples(ref, info["bytes_per_sample"]).tobytes()
         else:

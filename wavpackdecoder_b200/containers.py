@@ -11,9 +11,13 @@ produces (interleaved little-endian PCM; interleaved MSB-first DSD bytes):
   DFF  'FRM8' / 'DSD ' form with FVER, PROP('SND ': FS, CHNL, CMPR 'DSD ') and the 'DSD ' sound data chunk, big-endian
        64-bit sizes (DSDIFF 1.5 specification); sample data are the raw DSD bytes (WVB_OUT_DSD_RAW).
 
-DSF (Sony) stores each channel in 4096-byte blocks, LSB first; CAF is big-endian PCM: both need the audio re-laid-out,
-which is a different store pattern on the device, and are not built (the caller gets a NotImplementedError, never a
-silently wrong container).  Like the rest of wvdemo.py this is plumbing: no sample is touched on the host.
+  CAF  'caff' file header, 'desc' (sample rate as a 64-bit float, 'lpcm', little-endian flag, bytes per packet, channels,
+       bits) and 'data' (edit count 0) chunks with big-endian fields (Apple Core Audio Format specification); the PCM
+       itself stays little-endian, which the format flags allow.
+
+DSF (Sony) stores each channel in 4096-byte blocks, LSB first: that needs the audio re-laid-out, a different store pattern
+on the device, and is not built (the caller gets a NotImplementedError, never a silently wrong container).  Like the rest
+of wvdemo.py this is plumbing: no sample is touched on the host.
 """
 import struct
 
@@ -71,3 +75,12 @@ def dff_header(total_byte_times, num_channels, sample_rate):
 def dff_trailer(total_byte_times, num_channels):
     """IFF chunks are padded to an even length."""
     return bytes((total_byte_times * num_channels) & 1)
+
+
+def caf_header(total_samples, num_channels, sample_rate, bits, byteps, is_float=False):
+    """Core Audio Format header for `total_samples` frames of little-endian PCM: 8 + (12 + 32) + (12 + 4) = 68 bytes."""
+    flags = 2 | (1 if is_float else 0)  # kCAFLinearPCMFormatFlagIsLittleEndian | ...IsFloat
+    desc = struct.pack(">d4sIIIII", float(sample_rate), b"lpcm", flags, byteps * num_channels, 1, num_channels, bits)
+    data_bytes = total_samples * byteps * num_channels
+    return (b"caff" + struct.pack(">HH", 1, 0) + b"desc" + struct.pack(">q", len(desc)) + desc +
+            b"data" + struct.pack(">qI", 4 + data_bytes, 0))

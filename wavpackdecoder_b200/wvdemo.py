@@ -53,9 +53,11 @@ def native_container(wpc, total_samples, nch, byteps):
     if fmt == containers.WP_FORMAT_W64 and not dsd:
         return (containers.w64_header(total_samples, nch, rate, bits, byteps, bool(W.WavpackGetIsFloat(wpc))),
                 containers.w64_trailer(total_samples, nch, byteps))
+    if fmt == containers.WP_FORMAT_CAF and not dsd:
+        return containers.caf_header(total_samples, nch, rate, bits, byteps, bool(W.WavpackGetIsFloat(wpc))), b""
     if fmt == containers.WP_FORMAT_DFF and dsd:
         return containers.dff_header(total_samples, nch, rate), containers.dff_trailer(total_samples, nch)  # (the getter already reports the one-bit rate)
-    raise NotImplementedError("no header synthesis for file format %d (%s audio): DSF and CAF need the samples re-laid-out" %
+    raise NotImplementedError("no header synthesis for file format %d (%s audio): DSF needs the samples re-laid-out" %
                               (fmt, "DSD" if dsd else "PCM"))
 
 
@@ -64,7 +66,7 @@ def unpack_files(files, device=0, reference_quirks=True, container="reference"):
 
     container: "reference" writes what the demo writes (stored header, else RIFF/WAVE; DSD as offset-binary bytes);
     "native" is an extension: a stored header always passes through, otherwise the header of the format the file names is
-    synthesised (WAV, W64, DFF: containers.py), DSD bytes stay raw, and the demo's short-file quirk does not apply.
+    synthesised (WAV, W64, CAF, DFF: containers.py), DSD bytes stay raw, and the demo's short-file quirk does not apply.
 
     reference_quirks: files with fewer than 100 * SAMPLE_BUFFER_SIZE (409 600) samples, or of unknown length, make the reference demo throw
     DivideByZeroException at its progress print (`total_unpacked_samples % loop_samples`, WvDemo.cs:113,136) after the
