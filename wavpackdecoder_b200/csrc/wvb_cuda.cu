@@ -99,6 +99,7 @@ using FixS = wvb::FixedDecorr<true, WVB_FIXED_STEREO_TERMS>;
 using FixM = wvb::FixedDecorr<false, WVB_FIXED_MONO_TERMS>;
 using FixSB = wvb::FixedDecorr<true, WVB_FIXED_STEREO_B_TERMS>;
 using FixSC = wvb::FixedDecorr<true, WVB_FIXED_STEREO_C_TERMS>;
+using FixSD = wvb::FixedDecorr<true, WVB_FIXED_STEREO_D_TERMS>;
 
 } // namespace
 
@@ -198,6 +199,8 @@ pcm_kernel_t pcm_kernel(int variant)
     case wvb::V_STEREO | wvb::V_FIXED_B | wvb::V_F16: return k_decode_pcm<true, false, false, FixSB, 0, true>;
     case wvb::V_STEREO | wvb::V_FIXED_C: return k_decode_pcm<true, false, false, FixSC>;
     case wvb::V_STEREO | wvb::V_FIXED_C | wvb::V_F16: return k_decode_pcm<true, false, false, FixSC, 0, true>;
+    case wvb::V_STEREO | wvb::V_FIXED_D: return k_decode_pcm<true, false, false, FixSD>;
+    case wvb::V_STEREO | wvb::V_FIXED_D | wvb::V_F16: return k_decode_pcm<true, false, false, FixSD, 0, true>;
     case wvb::V_MONO | wvb::V_GENFIX: return k_decode_pcm<false, false, true, GenM>;
     case wvb::V_STEREO | wvb::V_GENFIX: return k_decode_pcm<true, false, true, GenS>;
     case wvb::V_MONO | wvb::V_GENFIX | wvb::V_HYBRID: return k_decode_pcm<false, true, true, GenM>;
@@ -244,15 +247,15 @@ void make_plan(const wvb_block_desc *descs, size_t n, int fmt, std::vector<uint3
         any_checksum |= (d.bflags & WVB_BF_BLOCK_CHECKSUM) != 0;
         int v = wvb::variant_of(d);
         // 16-bit interleaved stereo PCM gets its own launches: one aligned word store per frame, no byte-packing state
-        if ((v & ~(wvb::V_FIXED | wvb::V_FIXED_B | wvb::V_FIXED_C)) == wvb::V_STEREO && wvb::block_is_fast16(d, fmt == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : fmt)) v |= wvb::V_F16;
+        if ((v & ~wvb::V_ANY_FIXED) == wvb::V_STEREO && wvb::block_is_fast16(d, fmt == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : fmt)) v |= wvb::V_F16;
         // (the staged-output kernels keep a 16-slot ring in the column; the in-register ones reuse dead state slots for it)
-        const bool ring_in_class = WVB_STAGE_OUTPUT && (v & wvb::V_F16) && !(v & (wvb::V_FIXED | wvb::V_FIXED_B | wvb::V_FIXED_C));
+        const bool ring_in_class = WVB_STAGE_OUTPUT && (v & wvb::V_F16) && !(v & wvb::V_ANY_FIXED);
         int cls = v == wvb::V_DSD ? wvb::dsd_mode_class(d) : smem_class(std::max<int>(d.smem_words + (ring_in_class ? wvb::STAGE_RING_SLOTS : 0), (WVB_STAGE_OUTPUT && (v & wvb::V_F16)) ? wvb::STAGE_RING_SLOTS : 0));
         uint64_t clsbits = (uint64_t)(cls < 0 ? 1023 : cls) & 1023;
-        // variant | class | term signature (16 bits) | inverted length (so long blocks start first)
-        // variant (8 bits) | class (10) | term signature (16) | inverted length (30; longer blocks saturate, they only lose their order)
-        const uint64_t inv_len = 0x3fffffffu - (d.block_samples < 0x3fffffffu ? d.block_samples : 0x3fffffffu);
-        key[i] = ((uint64_t)v << 56) | (clsbits << 46) | ((uint64_t)(d.terms_sig & 0xffff) << 30) | inv_len;
+        // variant (10 bits) | class (10) | term signature (16) | inverted length (28; longer blocks saturate, they only lose
+        // their order), so that long blocks start first
+        const uint64_t inv_len = 0xfffffffu - (d.block_samples < 0xfffffffu ? d.block_samples : 0xfffffffu);
+        key[i] = ((uint64_t)v << 54) | (clsbits << 44) | ((uint64_t)(d.terms_sig & 0xffff) << 28) | inv_len;
     }
     // Ties keep the table's order, i.e. neighbouring blocks of the same files share a warp: their compressed streams and
     // their outputs lie next to each other in the slabs.  (Measured and rejected in round 2: ordering ties by compressed
@@ -263,9 +266,9 @@ void make_plan(const wvb_block_desc *descs, size_t n, int fmt, std::vector<uint3
     launches.clear();
     size_t i = 0;
     while (i < n) {
-        uint64_t k = key[order[i]] >> 46;
+        uint64_t k = key[order[i]] >> 44;
         size_t j = i;
-        while (j < n && (key[order[j]] >> 46) == k) j++;
+        while (j < n && (key[order[j]] >> 44) == k) j++;
         Launch L;
         L.variant = (int)(k >> 10);
         L.cls = (int)(k & 1023);

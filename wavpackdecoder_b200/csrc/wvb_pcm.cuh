@@ -518,7 +518,7 @@ template <bool STEREO, int... TERMS> struct FixedDecorr {
     static constexpr bool kFixed = true;
     static constexpr int N = (int)sizeof...(TERMS);
     int wA[N], wB[N];
-    uint32_t dl; // the N 3-bit deltas packed (N <= 10)
+    uint64_t dl; // the N 3-bit deltas packed (N <= 21)
     int hA[N][8], hB[N][8];
 
     static constexpr int term_at(int p)
@@ -540,7 +540,7 @@ template <bool STEREO, int... TERMS> struct FixedDecorr {
             const uint32_t d = match ? (uint32_t)SM(p) : 0u;
             if ((int)(d & 31u) - 5 != term) match = false;
             const int mask = (int)((d >> 8) & 7u), base = (int)(d >> 16);
-            dl |= ((d >> 5) & 7u) << (3 * p);
+            dl |= (uint64_t)((d >> 5) & 7u) << (3 * p);
             wA[p] = match ? SM(base) : 0;
             wB[p] = (STEREO && match) ? SM(base + 1) : 0;
             const int hb = base + (STEREO ? 2 : 1);
@@ -580,7 +580,7 @@ template <bool STEREO, int... TERMS> struct FixedDecorr {
     {
         constexpr int T[N] = {TERMS...};
         constexpr int term = T[P];
-        const int delta = (int)((dl >> (3 * P)) & 7u);
+        const int delta = (int)((uint32_t)(dl >> (3 * P)) & 7u);
         if (term > 0) {
             int s = predict<term>(hA[P]);
             const int oa = a + apply_weight(wA[P], s);

@@ -7,7 +7,8 @@
 namespace wvb {
 
 // kernel variants of the PCM path
-enum { V_MONO = 0, V_STEREO = 1, V_GENFIX = 2, V_HYBRID = 4, V_DSD = 8, V_FIXED = 16, V_F16 = 32, V_FIXED_B = 64, V_FIXED_C = 128, V_COUNT = 256,
+enum { V_MONO = 0, V_STEREO = 1, V_GENFIX = 2, V_HYBRID = 4, V_DSD = 8, V_FIXED = 16, V_F16 = 32, V_FIXED_B = 64, V_FIXED_C = 128, V_FIXED_D = 256,
+       V_COUNT = 512, V_ANY_FIXED = V_FIXED | V_FIXED_B | V_FIXED_C | V_FIXED_D,
        V_CHECKSUM = 200 /* not a decode variant: the block-checksum pass over a plan's blocks, queued after its decode launches */ };
 
 // FNV-1a over the term list in DECODER order, as wvb_index computes wvb_block_desc.terms_sig
@@ -30,6 +31,12 @@ constexpr uint32_t kFixedMonoSig = terms_hash(kFixedMono, 4);
 //   compression levels (tests/golden/ff_s16_stereo_c1.wv, ..._c0.wv); higher levels search a list per block and stay generic
 #define WVB_FIXED_STEREO_B_TERMS 3, 17, 2, 18, 18
 #define WVB_FIXED_STEREO_C_TERMS 17, 18
+//   stereo {18,18,2,3,-2,18,2,4,7,5,3,6,8,-1,18,2} (V_FIXED_D): the 16-term list of libwavpack's "very high" mode, the list of
+//   BASELINE configs[2]: 134 registers of weights and history, two 128-thread CTAs per SM -- and still twice as fast as the
+//   shared-memory kernel, whose pass costs ~65 instructions against ~20 here
+#define WVB_FIXED_STEREO_D_TERMS 2, 18, -1, 8, 6, 3, 5, 7, 4, 2, 18, -2, 3, 2, 18, 18
+constexpr int kFixedStereoD[] = {WVB_FIXED_STEREO_D_TERMS};
+constexpr uint32_t kFixedStereoDSig = terms_hash(kFixedStereoD, 16);
 constexpr int kFixedStereoB[] = {WVB_FIXED_STEREO_B_TERMS};
 constexpr int kFixedStereoC[] = {WVB_FIXED_STEREO_C_TERMS};
 constexpr uint32_t kFixedStereoBSig = terms_hash(kFixedStereoB, 5);
@@ -57,6 +64,7 @@ inline int variant_of(const wvb_block_desc &d)
         if (v == V_MONO && d.sub_len[WVB_SUB_TERMS] == 4 && d.terms_sig == kFixedMonoSig) v |= V_FIXED;
         if (v == V_STEREO && d.sub_len[WVB_SUB_TERMS] == 5 && d.terms_sig == kFixedStereoBSig) v |= V_FIXED_B;
         if (v == V_STEREO && d.sub_len[WVB_SUB_TERMS] == 2 && d.terms_sig == kFixedStereoCSig) v |= V_FIXED_C;
+        if (v == V_STEREO && d.sub_len[WVB_SUB_TERMS] == 16 && d.terms_sig == kFixedStereoDSig) v |= V_FIXED_D;
     }
     return v;
 }
