@@ -1,14 +1,9 @@
 #!/bin/bash
 # A/B of round-2 kernel changes on one box: alternative builds (WVB_LIB) / settings against the same synthetic batches
+T16=18,18,2,3,-2,18,2,4,7,5,3,6,8,-1,18,2
+D16=2,2,2,2,2,2,2,2,2,2,2,2,2,2,2,2
 run() { echo "== $*"; python tools/prof_run.py "$@" 2>&1 | grep -E "step [12]|flagged|Error|error"; }
-for sp in 0 auto; do
-  if [ $sp = auto ]; then unset WVB_SPREAD; else export WVB_SPREAD=$sp; fi
-  echo "WVB_SPREAD=$sp"
-  run --files 1 --seconds 60 --steps 3
-  run --files 16 --seconds 10 --steps 3
-  run --files 100 --seconds 10 --steps 3
-  run --files 500 --seconds 10 --steps 3
-  run --files 900 --seconds 10 --steps 3
-  run --files 100 --seconds 10 --steps 3 --kw bits=24
-  run --files 100 --seconds 10 --steps 3 --kw kind=1
-done
+run --files 3000 --seconds 10 --steps 3 --open-flags 0x8 --kw bits=24 channels=6 sample_rate=48000 block_samples=24000 terms=$T16 deltas=$D16
+run --files 2000 --seconds 10 --steps 3 --open-flags 0x10000 --kw bits=24 channels=6 sample_rate=48000 block_samples=24000 terms=$T16 deltas=$D16
+run --files 10000 --seconds 10 --steps 3 --kw terms=$T16 deltas=$D16
+run --files 4000 --seconds 10 --steps 3 --kw terms=$T16 deltas=$D16

@@ -205,6 +205,11 @@ pcm_kernel_t pcm_kernel(int variant)
     case wvb::V_STEREO | wvb::V_GENFIX: return k_decode_pcm<true, false, true, GenS>;
     case wvb::V_MONO | wvb::V_GENFIX | wvb::V_HYBRID: return k_decode_pcm<false, true, true, GenM>;
     case wvb::V_STEREO | wvb::V_GENFIX | wvb::V_HYBRID: return k_decode_pcm<true, true, true, GenS>;
+    // float / int32 / hybrid blocks with the stock term lists: the same fixup and entropy code over in-register decorrelation
+    case wvb::V_MONO | wvb::V_GENFIX | wvb::V_FIXED: return k_decode_pcm<false, false, true, FixM>;
+    case wvb::V_STEREO | wvb::V_GENFIX | wvb::V_FIXED: return k_decode_pcm<true, false, true, FixS>;
+    case wvb::V_MONO | wvb::V_GENFIX | wvb::V_HYBRID | wvb::V_FIXED: return k_decode_pcm<false, true, true, FixM>;
+    case wvb::V_STEREO | wvb::V_GENFIX | wvb::V_HYBRID | wvb::V_FIXED: return k_decode_pcm<true, true, true, FixS>;
     default: return nullptr;
     }
 }

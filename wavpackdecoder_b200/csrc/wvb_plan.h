@@ -58,13 +58,16 @@ inline int variant_of(const wvb_block_desc &d)
     int v = (d.flags & (4u | 0x40000000u)) ? V_MONO : V_STEREO;
     if (d.flags & 8u) v |= V_HYBRID | V_GENFIX;
     else if ((d.flags & (0x80u | 0x100u)) || (d.bflags & WVB_BF_WVX_PRESENT)) v |= V_GENFIX;
-    else if (!(d.bflags & (WVB_BF_MUTE_ALL | WVB_BF_STALE_STATE))) {
-        // plain lossless block: use the in-register kernel when its term list is one we specialise (checked again on the device)
-        if (v == V_STEREO && d.sub_len[WVB_SUB_TERMS] == 5 && d.terms_sig == kFixedStereoSig) v |= V_FIXED;
-        if (v == V_MONO && d.sub_len[WVB_SUB_TERMS] == 4 && d.terms_sig == kFixedMonoSig) v |= V_FIXED;
-        if (v == V_STEREO && d.sub_len[WVB_SUB_TERMS] == 5 && d.terms_sig == kFixedStereoBSig) v |= V_FIXED_B;
-        if (v == V_STEREO && d.sub_len[WVB_SUB_TERMS] == 2 && d.terms_sig == kFixedStereoCSig) v |= V_FIXED_C;
-        if (v == V_STEREO && d.sub_len[WVB_SUB_TERMS] == 16 && d.terms_sig == kFixedStereoDSig) v |= V_FIXED_D;
+    if (!(d.bflags & (WVB_BF_MUTE_ALL | WVB_BF_STALE_STATE))) {
+        // use an in-register kernel when the block's term list is one we specialise (checked again on the device).  The two
+        // stock lists also have hybrid and float / int32 instantiations; the other lists only plain lossless ones.
+        const bool plain = !(v & V_GENFIX);
+        const int base = v & V_STEREO;
+        if (base == V_STEREO && d.sub_len[WVB_SUB_TERMS] == 5 && d.terms_sig == kFixedStereoSig) v |= V_FIXED;
+        if (base == V_MONO && d.sub_len[WVB_SUB_TERMS] == 4 && d.terms_sig == kFixedMonoSig) v |= V_FIXED;
+        if (plain && base == V_STEREO && d.sub_len[WVB_SUB_TERMS] == 5 && d.terms_sig == kFixedStereoBSig) v |= V_FIXED_B;
+        if (plain && base == V_STEREO && d.sub_len[WVB_SUB_TERMS] == 2 && d.terms_sig == kFixedStereoCSig) v |= V_FIXED_C;
+        if (plain && base == V_STEREO && d.sub_len[WVB_SUB_TERMS] == 16 && d.terms_sig == kFixedStereoDSig) v |= V_FIXED_D;
     }
     return v;
 }
