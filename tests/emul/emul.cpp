@@ -58,6 +58,12 @@ extern "C" int emul_decode(const uint8_t *in, const wvb_block_desc *descs, size_
         case wvb::V_STEREO | wvb::V_GENFIX | wvb::V_FIXED:
             wvb::decode_block_pcm<true, false, true, HostSM, wvb::FixedDecorr<true, WVB_FIXED_STEREO_TERMS>>(sm, in, D, out, out_format, &r);
             break;
+        case wvb::V_MONO | wvb::V_GENFIX | wvb::V_HYBRID | wvb::V_FIXED:
+            wvb::decode_block_pcm<false, true, true, HostSM, wvb::FixedDecorr<false, WVB_FIXED_MONO_TERMS>>(sm, in, D, out, out_format, &r);
+            break;
+        case wvb::V_STEREO | wvb::V_GENFIX | wvb::V_HYBRID | wvb::V_FIXED:
+            wvb::decode_block_pcm<true, true, true, HostSM, wvb::FixedDecorr<true, WVB_FIXED_STEREO_TERMS>>(sm, in, D, out, out_format, &r);
+            break;
         case wvb::V_MONO | wvb::V_GENFIX: wvb::decode_block_pcm<false, false, true>(sm, in, D, out, out_format, &r); break;
         case wvb::V_STEREO | wvb::V_GENFIX: wvb::decode_block_pcm<true, false, true>(sm, in, D, out, out_format, &r); break;
         case wvb::V_MONO | wvb::V_GENFIX | wvb::V_HYBRID: wvb::decode_block_pcm<false, true, true>(sm, in, D, out, out_format, &r); break;

@@ -205,11 +205,15 @@ pcm_kernel_t pcm_kernel(int variant)
     case wvb::V_STEREO | wvb::V_GENFIX: return k_decode_pcm<true, false, true, GenS>;
     case wvb::V_MONO | wvb::V_GENFIX | wvb::V_HYBRID: return k_decode_pcm<false, true, true, GenM>;
     case wvb::V_STEREO | wvb::V_GENFIX | wvb::V_HYBRID: return k_decode_pcm<true, true, true, GenS>;
-    // float / int32 blocks with the stock term lists: the same fixup code over in-register decorrelation (float 89.6 -> 64.6 ms,
-    // int32 + WVX 107.5 -> 80.5 ms per 120 000 blocks).  The hybrid kernels gain nothing from it (154 ms either way: at 138
-    // registers they lose two of five resident CTAs) and stay on the shared-memory decorrelator.
+    // float / int32 / hybrid blocks with the stock term lists: the same fixup and entropy code over in-register decorrelation
+    // (float 89.6 -> 64.6 ms, int32 + WVX 107.5 -> 80.5 ms per 120 000 blocks).  The hybrid kernels carry more state and pay
+    // for the registers in resident CTAs; measured per register cap (generic / uncapped / 4 CTAs / 5 CTAs): stereo, 160 000
+    // blocks: 159.9 / 154 (138 registers) / 155.1 (128) / 214.6 ms (96, 292 B of spills); mono, 240 000 blocks:
+    // 114.5 / 104.6 (114) / 103.2 (118) / 94.6 ms (96, 44 B of spills).
     case wvb::V_MONO | wvb::V_GENFIX | wvb::V_FIXED: return k_decode_pcm<false, false, true, FixM>;
     case wvb::V_STEREO | wvb::V_GENFIX | wvb::V_FIXED: return k_decode_pcm<true, false, true, FixS>;
+    case wvb::V_MONO | wvb::V_GENFIX | wvb::V_HYBRID | wvb::V_FIXED: return k_decode_pcm<false, true, true, FixM, 5>;
+    case wvb::V_STEREO | wvb::V_GENFIX | wvb::V_HYBRID | wvb::V_FIXED: return k_decode_pcm<true, true, true, FixS, 4>;
     default: return nullptr;
     }
 }

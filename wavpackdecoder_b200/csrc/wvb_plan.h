@@ -60,11 +60,11 @@ inline int variant_of(const wvb_block_desc &d)
     else if ((d.flags & (0x80u | 0x100u)) || (d.bflags & WVB_BF_WVX_PRESENT)) v |= V_GENFIX;
     if (!(d.bflags & (WVB_BF_MUTE_ALL | WVB_BF_STALE_STATE))) {
         // use an in-register kernel when the block's term list is one we specialise (checked again on the device).  The two
-        // stock lists also have float / int32 instantiations; the other lists only plain lossless ones; hybrid stays generic.
-        const bool plain = !(v & V_GENFIX), stock_ok = !(v & V_HYBRID);
+        // stock lists also have float / int32 / hybrid instantiations; the other lists only plain lossless ones.
+        const bool plain = !(v & V_GENFIX);
         const int base = v & V_STEREO;
-        if (stock_ok && base == V_STEREO && d.sub_len[WVB_SUB_TERMS] == 5 && d.terms_sig == kFixedStereoSig) v |= V_FIXED;
-        if (stock_ok && base == V_MONO && d.sub_len[WVB_SUB_TERMS] == 4 && d.terms_sig == kFixedMonoSig) v |= V_FIXED;
+        if (base == V_STEREO && d.sub_len[WVB_SUB_TERMS] == 5 && d.terms_sig == kFixedStereoSig) v |= V_FIXED;
+        if (base == V_MONO && d.sub_len[WVB_SUB_TERMS] == 4 && d.terms_sig == kFixedMonoSig) v |= V_FIXED;
         if (plain && base == V_STEREO && d.sub_len[WVB_SUB_TERMS] == 5 && d.terms_sig == kFixedStereoBSig) v |= V_FIXED_B;
         if (plain && base == V_STEREO && d.sub_len[WVB_SUB_TERMS] == 2 && d.terms_sig == kFixedStereoCSig) v |= V_FIXED_C;
         if (plain && base == V_STEREO && d.sub_len[WVB_SUB_TERMS] == 16 && d.terms_sig == kFixedStereoDSig) v |= V_FIXED_D;
