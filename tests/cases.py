@@ -47,6 +47,12 @@ PCM_CASES = [
     ("hybrid", 0, 4096, dict(kind=KIND_HYBRID, terms=[18, 18, 2, 3])),
     ("hybrid_mono", 0, 4096, dict(kind=KIND_HYBRID, channels=1, terms=[18, 17, 2])),
     ("hybrid_neg", 0, 4096, dict(kind=KIND_HYBRID)),
+    # the stock term lists under hybrid / float / int32: fixup and entropy code over the in-register decorrelators
+    ("hybrid_mono_stock_terms", 0, 4096, dict(kind=KIND_HYBRID, channels=1, terms=[18, 18, 2, 3], deltas=[2] * 4)),
+    ("hybrid_stock_terms_balance_chunk999", 0, 999, dict(kind=KIND_HYBRID, hybrid_balance=1)),
+    ("hybrid_stock_terms_v402_24bit", 0, 4096, dict(kind=KIND_HYBRID, version=0x402, bits=24, hybrid_bitrate=6 * 256)),
+    ("float_mono_stock_terms", 0, 4096, dict(kind=KIND_FLOAT, bits=32, channels=1, terms=[18, 18, 2, 3], deltas=[2] * 4)),
+    ("int32_mono_stock_terms", 0, 4096, dict(bits=32, int32_sent_bits=8, channels=1, terms=[18, 18, 2, 3], deltas=[2] * 4)),
     ("hybrid_balance", 0, 4096, dict(kind=KIND_HYBRID, hybrid_balance=1, terms=[18, 2])),
     ("hybrid_2bit", 0, 4096, dict(kind=KIND_HYBRID, hybrid_bitrate=512, terms=[18, 2])),
     ("hybrid_8bit_src", 0, 4096, dict(kind=KIND_HYBRID, bits=8, hybrid_bitrate=768, terms=[17])),
