@@ -166,3 +166,16 @@ def test_device_checksum_at_every_slab_alignment():
             assert flagged == ([0] if damaged else []), (shift, flagged)
     finally:
         dec.close()
+
+
+@pytest.mark.gpu
+def test_verify_files_reports_block_checksum_errors():
+    from wavpackdecoder_b200.batch import verify_files
+    good = bytes(make_file(extras=X_RIFF_HEADER | X_CONFIG | X_BLOCK_CHECKSUM, seconds=0.6)[2])
+    blks = blocks_of(good)
+    bad = bytearray(good)
+    bad[blks[1][0] + blks[1][1] - 1] ^= 0x40  # the stored checksum of block 1: the audio still decodes cleanly
+    plain = bytes(make_file(extras=X_RIFF_HEADER | X_CONFIG, seconds=0.3)[2])
+    res = verify_files([good, bytes(bad), plain])
+    assert [r["block_checksum_errors"] for r in res] == [0, 1, None]
+    assert [r["crc_errors"] for r in res] == [0, 0, 0]

@@ -258,7 +258,8 @@ def verify_files(files, device=0):
     """Decode a list of .wv byte strings on the GPU and check each file against its stored MD5 without bringing the PCM
     back: the output slab stays in device memory, only 16 bytes per file and the per-block results return.
     Returns a list of dicts: md5 (hex of the decoded PCM), stored (hex or None), match (True/False/None when the file
-    stores no MD5), crc_errors, error (open error message or None).
+    stores no MD5), crc_errors, block_checksum_errors (blocks whose WavPack 5 ID_BLOCK_CHECKSUM does not match their bytes;
+    None when the file carries no such checksums), error (open error message or None).
     The stored digest covers the source file's audio bytes, so `match` is meaningful for lossless integer PCM; float
     sources (decoded to 24-bit integers here, as by the reference), hybrid-lossy and DSD files (stored digest over the DSD
     bytes; compare with an OUT_DSD_RAW decode instead) legitimately differ."""
@@ -278,12 +279,16 @@ def verify_files(files, device=0):
     finally:
         dec.close()
     res = []
+    table = N.desc_table(corpus.descs, corpus.nblocks) if corpus.nblocks else None
     for i in range(corpus.nfiles):
         info = corpus.infos[i]
         msg = bytes(info.error_message).split(b"\0", 1)[0].decode() or None
         f, c = int(corpus.first[i]), int(corpus.count[i])
         st = stored_md5(files[i])
         got = dig[i].tobytes()
+        has_ck = bool(c) and bool((table["bflags"][f:f + c] & N.BF_BLOCK_CHECKSUM).any())
         res.append(dict(md5=got.hex(), stored=st.hex() if st else None, match=None if (st is None or msg) else st == got,
-                        crc_errors=sum(1 for k in range(f, f + c) if results[k].rflags & N.RF_CRC_ERROR), error=msg))
+                        crc_errors=sum(1 for k in range(f, f + c) if results[k].rflags & N.RF_CRC_ERROR),
+                        block_checksum_errors=sum(1 for k in range(f, f + c) if results[k].rflags & N.RF_BLOCK_CHECKSUM) if has_ck else None,
+                        error=msg))
     return res
