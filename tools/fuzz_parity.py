@@ -16,7 +16,12 @@ from _harness import KIND_DSD, KIND_FLOAT, KIND_HYBRID, emul_decode_file, make_f
 BASES = [dict(), dict(channels=1), dict(bits=24), dict(kind=KIND_HYBRID), dict(bits=32, int32_sent_bits=8), dict(kind=KIND_FLOAT, bits=32),
          dict(terms=[17, 3, -1, 8]), dict(false_stereo=1), dict(kind=KIND_DSD, dsd_mode=1, block_samples=6000),
          dict(kind=KIND_DSD, dsd_mode=3, block_samples=6000), dict(kind=KIND_DSD, dsd_mode=0, block_samples=6000), dict(extras=1 | 2 | 4 | 8 | 16 | 64),
-         dict(terms=[18, 18, 2, 17, 3]), dict(terms=[18, 17]), dict(bits=8, channels=1), dict(bits=24, channels=1, block_samples=1001)]
+         dict(terms=[18, 18, 2, 17, 3]), dict(terms=[18, 17]), dict(bits=8, channels=1), dict(bits=24, channels=1, block_samples=1001),
+         # round 2: the 16-term in-register list, the stock lists under hybrid / float / int32 (in-register fixup kernels), mono
+         # blocks that start inside a caller's call (quirk C-5), block checksums
+         dict(terms=[18, 18, 2, 3, -2, 18, 2, 4, 7, 5, 3, 6, 8, -1, 18, 2], deltas=[2] * 16), dict(kind=KIND_HYBRID, channels=1, terms=[18, 18, 2, 3], deltas=[2] * 4),
+         dict(kind=KIND_FLOAT, bits=32, channels=1, terms=[18, 18, 2, 3], deltas=[2] * 4), dict(channels=1, block_samples=1000, terms=[18, 18, 2, 3], deltas=[2] * 4),
+         dict(channels=1, block_samples=700, bits=24), dict(extras=2 | 8, block_samples=3000)]
 
 
 def main():

@@ -75,7 +75,7 @@ template <int CTA, bool STAGED = false, int RESERVE = 0> struct SharedColumn {
 // CTA: threads per CTA.  Nothing in the decoder is CTA-wide (no barrier, no shared data between threads), so the CTA size
 // only sets the granularity at which shared memory and registers are handed out: blocks with long term lists (150-250
 // words of decorrelation state per thread) get one-warp CTAs, which fit 10 warps per SM where 128-thread CTAs fit 8.
-constexpr int CTA_SMALL = 32;
+constexpr int CTA_SMALL = 32, CTA_FIXED_D = 64;
 template <bool STEREO, bool HYB, bool GENFIX, class DEC, int MINB = 0, bool F16 = false, int CTA = CTA_THREADS>
 __global__ void __launch_bounds__(CTA, MINB)
 k_decode_pcm(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ descs, const uint32_t *__restrict__ order,
@@ -199,8 +199,10 @@ pcm_kernel_t pcm_kernel(int variant)
     case wvb::V_STEREO | wvb::V_FIXED_B | wvb::V_F16: return k_decode_pcm<true, false, false, FixSB, 0, true>;
     case wvb::V_STEREO | wvb::V_FIXED_C: return k_decode_pcm<true, false, false, FixSC>;
     case wvb::V_STEREO | wvb::V_FIXED_C | wvb::V_F16: return k_decode_pcm<true, false, false, FixSC, 0, true>;
-    case wvb::V_STEREO | wvb::V_FIXED_D: return k_decode_pcm<true, false, false, FixSD>;
-    case wvb::V_STEREO | wvb::V_FIXED_D | wvb::V_F16: return k_decode_pcm<true, false, false, FixSD, 0, true>;
+    // the 16-term list: 228-255 registers, i.e. 256 resident threads per SM whatever the CTA size; in 64-thread CTAs the
+    // launch tail is finer (76.5 vs 79.0 ms per 60 000 blocks).  Capping the registers for a fifth CTA spills the history: 244 ms.
+    case wvb::V_STEREO | wvb::V_FIXED_D: return k_decode_pcm<true, false, false, FixSD, 4, false, CTA_FIXED_D>;
+    case wvb::V_STEREO | wvb::V_FIXED_D | wvb::V_F16: return k_decode_pcm<true, false, false, FixSD, 4, true, CTA_FIXED_D>;
     case wvb::V_MONO | wvb::V_GENFIX: return k_decode_pcm<false, false, true, GenM>;
     case wvb::V_STEREO | wvb::V_GENFIX: return k_decode_pcm<true, false, true, GenS>;
     case wvb::V_MONO | wvb::V_GENFIX | wvb::V_HYBRID: return k_decode_pcm<false, true, true, GenM>;
@@ -491,7 +493,8 @@ static int launch_plan(wvb_batch *b, const std::vector<Launch> &plan, const uint
         }
         pcm_kernel_t k = pcm_kernel(L.variant);
         int cta = CTA_THREADS;
-        if (L.cls > SMEM_CLASS_SMALL_CTA) {
+        if (L.variant & wvb::V_FIXED_D) cta = CTA_FIXED_D;
+        else if (L.cls > SMEM_CLASS_SMALL_CTA) {
             pcm_kernel_t ks = pcm_kernel_small(L.variant);
             if (ks) { k = ks; cta = CTA_SMALL; }
         }
@@ -500,7 +503,7 @@ static int launch_plan(wvb_batch *b, const std::vector<Launch> &plan, const uint
         if (smem > b->smem_optin) return set_error(WVB_E_ARG, "shared memory class exceeds the device limit");
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // (left alone, the driver sizes the shared-memory carve-out for fewer CTAs than the state allows)
-        if (cta == CTA_SMALL) CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        if (cta != CTA_THREADS) CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         const uint32_t spread = pick_spread(L.count, b->sm_count);
         unsigned grid = (unsigned)((((uint64_t)L.count << spread) + cta - 1) / cta);
         k<<<grid, cta, smem, s>>>(din, b->d_descs, b->d_order + L.first, L.count, dout, fmt == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : fmt, dres, spread);
