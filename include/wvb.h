@@ -304,6 +304,14 @@ int wvb_batch_decode_files(wvb_batch *b, const uint8_t *slab, size_t slab_bytes,
                            wvb_block_desc *blocks, size_t cap, uint64_t *first, uint64_t *count, uint64_t *file_out_offset, size_t *nblocks,
                            uint64_t *out_bytes, void *out, size_t out_cap, uint32_t mem_flags, wvb_block_result *results);
 
+/* Container writer, DSD (beyond the reference, whose demo writes RIFF only, WvDemo.cs:78-105): re-lay decoded DSD bytes
+ * (WVB_OUT_DSD_RAW: one byte per channel per byte-time, interleaved, oldest bit in the MSB -- the DSDIFF layout) into the
+ * Sony DSF layout (4096-byte blocks per channel, oldest bit in the LSB, last block zero padded) on the device.  File i:
+ * frames[i] byte-times of channels[i] channels at device_src + src_off[i]  ->  ceil(frames/4096) * 4096 * channels bytes
+ * at device_dst + dst_off[i] (4-byte aligned).  Both slabs are device memory. */
+int wvb_batch_dsd_to_dsf(wvb_batch *b, const void *device_src, size_t src_bytes, void *device_dst, size_t dst_bytes, const uint64_t *src_off,
+                         const uint64_t *dst_off, const uint64_t *frames, const uint32_t *channels, size_t nfiles);
+
 /* pinned host memory helpers for hosts without their own allocator (C# shim) */
 void *wvb_host_alloc(size_t bytes);
 void wvb_host_free(void *p);

@@ -86,6 +86,29 @@ def test_caf_header_round_trip():
         assert h[52:56] == b"data" and struct.unpack_from(">qI", h, 56) == (4 + n * ch * byteps, 0)
 
 
+def dsf_layout(raw, frames, ch):
+    """numpy restatement of the DSF data layout: per-channel 4096-byte blocks, bits reversed, last block zero padded."""
+    a = np.frombuffer(raw, dtype=np.uint8).reshape(frames, ch)
+    rev = np.array([int("{:08b}".format(i)[::-1], 2) for i in range(256)], dtype=np.uint8)
+    groups = (frames + 4095) // 4096
+    padded = np.zeros((groups * 4096, ch), dtype=np.uint8)
+    padded[:frames] = rev[a]
+    return padded.reshape(groups, 4096, ch).transpose(0, 2, 1).tobytes()
+
+
+def test_dsf_header_layout():
+    from wavpackdecoder_b200 import containers as K
+    for n, ch, rate in [(4096, 2, 2822400), (4097, 1, 2822400), (10000, 6, 5644800), (1, 2, 2822400)]:
+        h = K.dsf_header(n, ch, rate)
+        data = K.dsf_data_bytes(n, ch)
+        assert len(h) == 92 and data == (n + 4095) // 4096 * 4096 * ch
+        assert struct.unpack_from("<4sQQQ", h, 0) == (b"DSD ", 28, 92 + data, 0)
+        tag, size, ver, fid, ctype, nch, fs, bps, count, blk, rsv = struct.unpack_from("<4sQIIIIIIQII", h, 28)
+        assert (tag, size, ver, fid, nch, fs, bps, count, blk, rsv) == (b"fmt ", 52, 1, 0, ch, rate, 1, n * 8, 4096, 0)
+        assert ctype == {1: 1, 2: 2, 6: 7}[ch]
+        assert struct.unpack_from("<4sQ", h, 80) == (b"data", 12 + data)
+
+
 def _with_file_format(data, fmt):
     """Set the file_format byte of the ID_NEW_CONFIG_BLOCK the synthetic encoder writes (one payload byte, odd-size flag)."""
     data = bytearray(data)
@@ -106,10 +129,12 @@ def test_native_containers_on_device():
     caf = _with_file_format(make_file(extras=X_CONFIG | X_NEW_CONFIG, bits=24, seconds=0.2)[2], K.WP_FORMAT_CAF)
     dsd = _with_file_format(make_file(kind=KIND_DSD, dsd_mode=1, extras=X_CONFIG | X_NEW_CONFIG, seconds=0.05, block_samples=4000)[2], K.WP_FORMAT_DFF)
     dsd_mono = _with_file_format(make_file(kind=KIND_DSD, dsd_mode=3, channels=1, extras=X_CONFIG | X_NEW_CONFIG, nsamples=4097, block_samples=2000)[2], K.WP_FORMAT_DFF)
-    files = [pcm16, pcm24, wav, stored, dsd, dsd_mono, caf]
+    dsf = make_file(kind=KIND_DSD, dsd_mode=1, extras=X_CONFIG | X_NEW_CONFIG, nsamples=9000, block_samples=4000)[2]  # (the encoder writes DSF)
+    dsf_mono = make_file(kind=KIND_DSD, dsd_mode=0, channels=1, extras=X_CONFIG | X_NEW_CONFIG, nsamples=4096, block_samples=2048)[2]
+    files = [pcm16, pcm24, wav, stored, dsd, dsd_mono, caf, bytes(dsf), bytes(dsf_mono)]
     res = unpack_files(files, container="native")
     assert [code for _b, code in res] == [0] * len(files)
-    for data, (blob, _code), kind in zip(files, res, ["w64", "w64", "wav", "stored", "dff", "dff", "caf"]):
+    for data, (blob, _code), kind in zip(files, res, ["w64", "w64", "wav", "stored", "dff", "dff", "caf", "dsf", "dsf"]):
         ref, errs, status, info = oracle_decode(data)
         assert status == 0 and errs == 0
         if kind == "w64":
@@ -117,6 +142,12 @@ def test_native_containers_on_device():
             do, dl = chunks["data"]
             assert blob[do:do + dl] == format_samples(ref, info["bytes_per_sample"]).tobytes()
             assert struct.unpack_from("<HHI", blob, chunks["fmt "][0]) == (1, info["reduced_channels"], info["sample_rate"])
+        elif kind == "dsf":
+            raw = np.asarray(ref, dtype=np.uint8).tobytes()
+            ch = info["reduced_channels"]
+            frames = len(raw) // ch
+            assert blob[:92] == K.dsf_header(frames, ch, info["sample_rate"])
+            assert blob[92:] == dsf_layout(raw, frames, ch)
         elif kind == "caf":
             assert blob[:4] == b"caff" and blob[68:] == format_samples(ref, info["bytes_per_sample"]).tobytes()
             assert struct.unpack_from(">q", blob, 56)[0] == 4 + len(blob) - 68
@@ -129,5 +160,5 @@ def test_native_containers_on_device():
             po, ps = top[b"PROP"]
             prop = {cid: (o, s) for cid, o, s in parse_iff(blob, po + 4, po + ps)}
             assert struct.unpack_from(">I", blob, prop[b"FS  "][0])[0] == info["sample_rate"]
-    with pytest.raises(NotImplementedError):
-        unpack_files([_with_file_format(dsd, K.WP_FORMAT_DSF)], container="native")
+    with pytest.raises(NotImplementedError):  # PCM audio in a file that names a DSD container
+        unpack_files([_with_file_format(pcm16, K.WP_FORMAT_DSF)], container="native")

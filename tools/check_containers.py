@@ -70,6 +70,15 @@ def main():
         ("w64 24-bit mono", "w64", K.w64_header(999, 1, 48000, 24, 3) + pcm[:2997] + K.w64_trailer(999, 1, 3), pcm[:2997], 48000, 1),
         ("dff", "iff", K.dff_header(nd, 2, 2822400) + dsd + K.dff_trailer(nd, 2), dsd, 2822400 // 8, 2),
     ]
+    # DSF: the data chunk holds the re-laid-out bytes (wvb_batch_dsd_to_dsf on the device; here tests/test_containers.py's numpy
+    # restatement of the layout), which FFmpeg's dsf demuxer hands out block by block as they are stored
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_containers import dsf_layout
+    dsf_data = dsf_layout(dsd, nd, 2)
+    # (FFmpeg's demuxer drops the zero padding of the last block group: each channel's valid bytes, channel after channel)
+    groups, valid = (nd + 4095) // 4096, nd - (nd + 4095) // 4096 * 4096 + 4096
+    expect = dsf_data[:(groups - 1) * 8192] + b"".join(dsf_data[(groups - 1) * 8192 + c * 4096:(groups - 1) * 8192 + c * 4096 + valid] for c in range(2))
+    cases.append(("dsf", "dsf", K.dsf_header(nd, 2, 2822400) + dsf_data, expect, 2822400 // 8, 2))
     for name, demuxer, blob, audio, rate, ch in cases:
         with tempfile.NamedTemporaryFile(suffix="." + name.split()[0], delete=False) as f:
             f.write(blob)

@@ -82,7 +82,7 @@ assert C.sizeof(BlockResult) == 16
 EXPORTS = [
     "wvb_abi_version", "wvb_abi_layout", "wvb_last_error", "wvb_device_count", "wvb_index", "wvb_index_seek", "wvb_index_many", "wvb_rebase", "wvb_frame_bytes",
     "wvb_batch_create", "wvb_batch_destroy", "wvb_batch_prepare", "wvb_batch_decode", "wvb_batch_wait", "wvb_batch_timing", "wvb_batch_stream",
-    "wvb_host_alloc", "wvb_host_free", "wvb_batch_md5", "wvb_stored_md5", "wvb_block_checksum_ok", "wvb_batch_decode_files",
+    "wvb_host_alloc", "wvb_host_free", "wvb_batch_md5", "wvb_stored_md5", "wvb_block_checksum_ok", "wvb_batch_decode_files", "wvb_batch_dsd_to_dsf",
 ]
 
 
@@ -155,6 +155,8 @@ def load():
                                            C.c_int, C.POINTER(FileInfo), C.POINTER(BlockDesc), C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.POINTER(C.c_size_t), C.POINTER(C.c_uint64), C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]
     lib.wvb_batch_decode_files.restype = C.c_int
+    lib.wvb_batch_dsd_to_dsf.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.wvb_batch_dsd_to_dsf.restype = C.c_int
     lib.wvb_batch_prepare.argtypes = [C.c_void_p, C.POINTER(BlockDesc), C.c_size_t, C.c_int]
     lib.wvb_batch_prepare.restype = C.c_int
     lib.wvb_batch_wait.argtypes = [C.c_void_p]

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwvb.so")
 SOURCES = ["wvb_cuda.cu", "wvb_index.cpp"]
-HEADERS = ["wvb_pcm.cuh", "wvb_checksum.cuh", "wvb_dsd.cuh", "wvb_dsd_core.cuh", "wvb_grid.h", "wvb_md5.cuh", "wvb_plan.h", "wv_tables.h", os.path.join("..", "..", "include", "wvb.h")]
+HEADERS = ["wvb_pcm.cuh", "wvb_checksum.cuh", "wvb_dsf.cuh", "wvb_dsd.cuh", "wvb_dsd_core.cuh", "wvb_grid.h", "wvb_md5.cuh", "wvb_plan.h", "wv_tables.h", os.path.join("..", "..", "include", "wvb.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-shared", "-Xcompiler", "-fPIC,-fwrapv,-O2",
     "-cudart", "static", "--expt-relaxed-constexpr", "-Xptxas", "-v",

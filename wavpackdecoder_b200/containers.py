@@ -15,9 +15,12 @@ produces (interleaved little-endian PCM; interleaved MSB-first DSD bytes):
        bits) and 'data' (edit count 0) chunks with big-endian fields (Apple Core Audio Format specification); the PCM
        itself stays little-endian, which the format flags allow.
 
-DSF (Sony) stores each channel in 4096-byte blocks, LSB first: that needs the audio re-laid-out, a different store pattern
-on the device, and is not built (the caller gets a NotImplementedError, never a silently wrong container).  Like the rest
-of wvdemo.py this is plumbing: no sample is touched on the host.
+  DSF  'DSD ' (28 bytes), 'fmt ' (52 bytes: format version 1, DSD raw, channel type and count, one-bit sampling frequency,
+       1 bit per sample, one-bit sample count per channel, 4096-byte blocks) and 'data' chunks, little-endian (Sony DSF
+       specification 1.01).  DSF stores each channel in 4096-byte blocks, oldest bit in the LSB: the decoded bytes are re-laid
+       out on the device (wvb_batch_dsd_to_dsf, wvb_dsf.cuh).
+
+Like the rest of wvdemo.py this is plumbing: no sample is touched by host arithmetic.
 """
 import struct
 
@@ -84,3 +87,19 @@ def caf_header(total_samples, num_channels, sample_rate, bits, byteps, is_float=
     data_bytes = total_samples * byteps * num_channels
     return (b"caff" + struct.pack(">HH", 1, 0) + b"desc" + struct.pack(">q", len(desc)) + desc +
             b"data" + struct.pack(">qI", 4 + data_bytes, 0))
+
+
+DSF_BLOCK = 4096
+_DSF_CHANNEL_TYPE = {1: 1, 2: 2, 3: 3, 4: 4, 5: 6, 6: 7}  # mono, stereo, 3 channels, quad, 5 channels, 5.1 (4 channels: quad)
+
+
+def dsf_data_bytes(total_byte_times, num_channels):
+    return (total_byte_times + DSF_BLOCK - 1) // DSF_BLOCK * DSF_BLOCK * num_channels
+
+
+def dsf_header(total_byte_times, num_channels, sample_rate):
+    """Sony DSF header (92 bytes) for `total_byte_times` bytes per channel; sample_rate is the one-bit rate in Hz."""
+    data = dsf_data_bytes(total_byte_times, num_channels)
+    fmt = struct.pack("<4sQIIIIIIQII", b"fmt ", 52, 1, 0, _DSF_CHANNEL_TYPE.get(num_channels, 7), num_channels, sample_rate & 0xffffffff, 1,
+                      total_byte_times * 8, DSF_BLOCK, 0)
+    return struct.pack("<4sQQQ", b"DSD ", 28, 28 + 52 + 12 + data, 0) + fmt + struct.pack("<4sQ", b"data", 12 + data)

@@ -22,6 +22,7 @@
 
 #include "wvb_checksum.cuh"
 #include "wvb_dsd.cuh"
+#include "wvb_dsf.cuh"
 #include "wvb_md5.cuh"
 #include "wvb_pcm.cuh"
 #include "wvb_plan.h"
@@ -1011,6 +1012,39 @@ int wvb_batch_decode_files(wvb_batch *b, const uint8_t *slab, size_t slab_bytes,
     CUDA_TRY(cudaEventRecord(b->ev[3], s));
     b->timed = true;
     if (!(mem_flags & WVB_NO_SYNC)) return wvb_batch_wait(b);
+    return WVB_OK;
+}
+
+int wvb_batch_dsd_to_dsf(wvb_batch *b, const void *device_src, size_t src_bytes, void *device_dst, size_t dst_bytes, const uint64_t *src_off,
+                         const uint64_t *dst_off, const uint64_t *frames, const uint32_t *channels, size_t nfiles)
+{
+    if (!b || !device_src || !device_dst || !src_off || !dst_off || !frames || !channels) return WVB_E_ARG;
+    if (!nfiles) return WVB_OK;
+    if (nfiles > 0xffffffu) return WVB_E_ARG;
+    CUDA_TRY(cudaSetDevice(b->device));
+    std::vector<wvb::DsfJob> jobs(nfiles);
+    uint64_t words = 0;
+    for (size_t i = 0; i < nfiles; i++) {
+        if (channels[i] == 0 || channels[i] > 255) return set_error(WVB_E_ARG, "wvb_batch_dsd_to_dsf: channel count not in 1..255");
+        const uint64_t in_len = frames[i] * channels[i];
+        const uint64_t out_len = (frames[i] + wvb::DSF_BLOCK - 1) / wvb::DSF_BLOCK * wvb::DSF_BLOCK * channels[i];
+        if (src_off[i] > src_bytes || in_len > src_bytes - src_off[i] || dst_off[i] > dst_bytes || out_len > dst_bytes - dst_off[i] || (dst_off[i] & 3))
+            return set_error(WVB_E_ARG, "wvb_batch_dsd_to_dsf: range outside the slabs (or destination not 4-byte aligned)");
+        if (words > 0xffffffffull) return set_error(WVB_E_ARG, "wvb_batch_dsd_to_dsf: more than 16 GiB of DSF data in one call");
+        jobs[i] = wvb::DsfJob{src_off[i], dst_off[i], frames[i], channels[i], (uint32_t)words};
+        words += out_len / 4;
+    }
+    if (!words) return WVB_OK;
+    int rc;
+    if ((rc = ensure(b->d_md5_ranges, b->d_md5_ranges_cap, nfiles * sizeof(wvb::DsfJob) / sizeof(uint64_t) + 1)) != WVB_OK) return rc;
+    cudaStream_t s = b->stream;
+    CUDA_TRY(cudaMemcpyAsync(b->d_md5_ranges, jobs.data(), nfiles * sizeof(wvb::DsfJob), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s)); // (jobs is a local vector)
+    wvb::k_dsd_to_dsf<<<(unsigned)((words + wvb::DSF_THREADS - 1) / wvb::DSF_THREADS), wvb::DSF_THREADS, 0, s>>>(
+        (const uint8_t *)device_src, (uint8_t *)device_dst, (const wvb::DsfJob *)b->d_md5_ranges, (uint32_t)nfiles, words);
+    CUDA_TRY(cudaGetLastError());
+    b->launches++;
+    CUDA_TRY(cudaStreamSynchronize(s));
     return WVB_OK;
 }
 

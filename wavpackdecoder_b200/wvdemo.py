@@ -57,8 +57,38 @@ def native_container(wpc, total_samples, nch, byteps):
         return containers.caf_header(total_samples, nch, rate, bits, byteps, bool(W.WavpackGetIsFloat(wpc))), b""
     if fmt == containers.WP_FORMAT_DFF and dsd:
         return containers.dff_header(total_samples, nch, rate), containers.dff_trailer(total_samples, nch)  # (the getter already reports the one-bit rate)
-    raise NotImplementedError("no header synthesis for file format %d (%s audio): DSF needs the samples re-laid-out" %
-                              (fmt, "DSD" if dsd else "PCM"))
+    if fmt == containers.WP_FORMAT_DSF and dsd:
+        return containers.dsf_header(total_samples, nch, rate), DSF_RELAYOUT  # the data follow from the device re-layout pass
+    raise NotImplementedError("no header synthesis for file format %d with %s audio" % (fmt, "DSD" if dsd else "PCM"))
+
+
+DSF_RELAYOUT = object()  # marker returned in place of a trailer: the file's DSD bytes go through wvb_batch_dsd_to_dsf
+
+
+def _dsf_relayout(dec, out, jobs):
+    """jobs: [(offset of the file's raw DSD bytes in `out`, byte-times, channels)].  Uploads those ranges, re-lays them out on
+    the device and returns one uint8 array per job (ceil(frames / 4096) * 4096 * channels bytes)."""
+    import ctypes as C
+    import torch
+    dev = torch.device("cuda", dec.device)
+    src_off, dst_off, spos, dpos = [], [], 0, 0
+    for _o, frames, ch in jobs:
+        src_off.append(spos); dst_off.append(dpos)
+        spos += (frames * ch + 15) & ~15
+        dpos += containers.dsf_data_bytes(frames, ch)
+    src = np.zeros(max(spos, 16), dtype=np.uint8)
+    for (o, frames, ch), so in zip(jobs, src_off):
+        src[so:so + frames * ch] = out[o:o + frames * ch]
+    d_src = torch.from_numpy(src).to(dev)
+    d_dst = torch.empty(max(dpos, 16), dtype=torch.uint8, device=dev)
+    a_src, a_dst = np.array(src_off, dtype=np.uint64), np.array(dst_off, dtype=np.uint64)
+    a_fr, a_ch = np.array([j[1] for j in jobs], dtype=np.uint64), np.array([j[2] for j in jobs], dtype=np.uint32)
+    rc = dec.lib.wvb_batch_dsd_to_dsf(dec.h, d_src.data_ptr(), d_src.numel(), d_dst.data_ptr(), d_dst.numel(), a_src.ctypes.data, a_dst.ctypes.data,
+                                      a_fr.ctypes.data, a_ch.ctypes.data, len(jobs))
+    if rc != N.OK:
+        raise RuntimeError("wvb_batch_dsd_to_dsf failed: %d %s" % (rc, (dec.lib.wvb_last_error() or b"").decode()))
+    host = d_dst.cpu().numpy()
+    return [host[do:do + containers.dsf_data_bytes(fr, ch)] for (_o, fr, ch), do in zip(jobs, dst_off)]
 
 
 def unpack_files(files, device=0, reference_quirks=True, container="reference"):
@@ -66,7 +96,7 @@ def unpack_files(files, device=0, reference_quirks=True, container="reference"):
 
     container: "reference" writes what the demo writes (stored header, else RIFF/WAVE; DSD as offset-binary bytes);
     "native" is an extension: a stored header always passes through, otherwise the header of the format the file names is
-    synthesised (WAV, W64, CAF, DFF: containers.py), DSD bytes stay raw, and the demo's short-file quirk does not apply.
+    synthesised (WAV, W64, CAF, DFF, DSF: containers.py), DSD bytes stay raw, and the demo's short-file quirk does not apply.
 
     reference_quirks: files with fewer than 100 * SAMPLE_BUFFER_SIZE (409 600) samples, or of unknown length, make the reference demo throw
     DivideByZeroException at its progress print (`total_unpacked_samples % loop_samples`, WvDemo.cs:113,136) after the
@@ -82,6 +112,7 @@ def unpack_files(files, device=0, reference_quirks=True, container="reference"):
     nfiles = corpus.nfiles
     ctxs = [_context(corpus, i) for i in range(nfiles)]
     heads, tails, pcm_bytes, ok = [], [], [], []
+    dsf_files = {}  # file index -> (byte-times, channels): DSD data to be re-laid-out for the DSF container
     for i, wpc in enumerate(ctxs):
         if W.WavpackGetErrorMessage(wpc):  # WvDemo.cs:41-46: no output file at all
             heads.append(b""); tails.append(b""); pcm_bytes.append(0); ok.append(False)
@@ -96,6 +127,9 @@ def unpack_files(files, device=0, reference_quirks=True, container="reference"):
         elif native:
             h, pad = native_container(wpc, int(wpc.info.indexed_samples), nch, byteps)
             heads.append(h)
+            if pad is DSF_RELAYOUT:
+                dsf_files[i] = (int(wpc.info.indexed_samples), nch)
+                pad = b""
         else:
             heads.append(wave_header(W.WavpackGetNumSamples(wpc, True), nch, W.WavpackGetSampleRate(wpc),
                                      W.WavpackGetBitsPerSample(wpc), byteps))
@@ -119,10 +153,15 @@ def unpack_files(files, device=0, reference_quirks=True, container="reference"):
 
     out = np.zeros(total + 64, dtype=np.uint8)
     results = (N.BlockResult * max(corpus.nblocks, 1))()
+    dsf_data = {}
     if corpus.nblocks:
         dec = BatchDecoder(device)
         try:
             dec.decode(corpus.slab.ctypes.data, corpus.slab.size, corpus.descs, corpus.nblocks, out.ctypes.data, total, out_format, 0, results)
+            if dsf_files:
+                order = sorted(dsf_files)
+                arrays = _dsf_relayout(dec, out, [(int(pcm_start[i]),) + dsf_files[i] for i in order])
+                dsf_data = dict(zip(order, arrays))
         finally:
             dec.close()
 
@@ -147,6 +186,9 @@ def unpack_files(files, device=0, reference_quirks=True, container="reference"):
             continue
         num_samples = W.WavpackGetNumSamples(wpc)
         code = 1 if (num_samples != -1 and unpacked != num_samples) or crc_errors > 0 else 0  # WvDemo.cs:157-169
+        if i in dsf_data:
+            res.append((h + dsf_data[i].tobytes() + t, code))
+            continue
         res.append((out[s - len(h):s + pcm_bytes[i] + len(t)].tobytes(), code))
     return res
 
