@@ -30,7 +30,7 @@
 namespace {
 
 #ifndef WVB_CTA
-#define WVB_CTA 128
+#define WVB_CTA 32 // threads per decode CTA: one warp (measured against 64 / 128: 76.9 / 77.1 / 77.8 ms on the bench launch, see k_decode_pcm)
 #endif
 #ifndef WVB_STAGE_OUTPUT
 #define WVB_STAGE_OUTPUT 1 // 0: experiment builds without the shared-memory output staging of the 16-bit stereo kernels
@@ -74,8 +74,9 @@ template <int CTA, bool STAGED = false, int RESERVE = 0> struct SharedColumn {
 };
 
 // CTA: threads per CTA.  Nothing in the decoder is CTA-wide (no barrier, no shared data between threads), so the CTA size
-// only sets the granularity at which shared memory and registers are handed out: blocks with long term lists (150-250
-// words of decorrelation state per thread) get one-warp CTAs, which fit 10 warps per SM where 128-thread CTAs fit 8.
+// only sets the granularity at which shared memory and registers are handed out and at which a launch's tail drains.
+// One-warp CTAs are the default: blocks with long term lists (150-250 words of decorrelation state per thread) fit 10 warps
+// per SM that way where 128-thread CTAs fit 8, and the 88-register kernels 23 warps instead of 20.
 constexpr int CTA_SMALL = 32, CTA_FIXED_D = 64;
 template <bool STEREO, bool HYB, bool GENFIX, class DEC, int MINB = 0, bool F16 = false, int CTA = CTA_THREADS>
 __global__ void __launch_bounds__(CTA, MINB)
@@ -504,7 +505,7 @@ static int launch_plan(wvb_batch *b, const std::vector<Launch> &plan, const uint
         if (smem > b->smem_optin) return set_error(WVB_E_ARG, "shared memory class exceeds the device limit");
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // (left alone, the driver sizes the shared-memory carve-out for fewer CTAs than the state allows)
-        if (cta != CTA_THREADS) CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        if (L.cls > SMEM_CLASS_SMALL_CTA) CUDA_TRY(cudaFuncSetAttribute((const void *)k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         const uint32_t spread = pick_spread(L.count, b->sm_count);
         unsigned grid = (unsigned)((((uint64_t)L.count << spread) + cta - 1) / cta);
         k<<<grid, cta, smem, s>>>(din, b->d_descs, b->d_order + L.first, L.count, dout, fmt == WVB_OUT_DSD_RAW ? WVB_OUT_PCM : fmt, dres, spread);
