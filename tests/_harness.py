@@ -189,7 +189,7 @@ class OracleFile:
             sample_rate=L.rd_get_sample_rate(self.ctx), num_channels=L.rd_get_num_channels(self.ctx),
             reduced_channels=L.rd_get_reduced_channels(self.ctx), bits_per_sample=L.rd_get_bits_per_sample(self.ctx),
             bytes_per_sample=L.rd_get_bytes_per_sample(self.ctx), lossy=bool(L.rd_lossy(self.ctx)),
-            file_format=L.rd_get_file_format(self.ctx), file_extension=L.rd_get_file_extension(self.ctx).decode(),
+            file_format=L.rd_get_file_format(self.ctx), file_extension=L.rd_get_file_extension(self.ctx).decode("utf-8", "replace"),
             is_five=bool(L.rd_get_is_five(self.ctx)), version=L.rd_get_version(self.ctx),
             is_float=bool(L.rd_get_is_float(self.ctx)), mode=L.rd_get_mode(self.ctx),
             compression_level=lvl.value.decode() or None,
