@@ -108,7 +108,7 @@ namespace WavPack
         // container writer, DSD: decoded DSD bytes (DSDIFF layout) re-laid-out for Sony DSF on the device
         [DllImport(Lib)] internal static extern unsafe int wvb_batch_dsd_to_dsf(IntPtr batch, void* device_src, UIntPtr src_bytes, void* device_dst, UIntPtr dst_bytes,
             ulong* src_off, ulong* dst_off, ulong* frames, uint* channels, UIntPtr nfiles);
-        internal const int WVB_ABI_VERSION = 2;
+        internal const int WVB_ABI_VERSION = 3;
         internal const int WVB_OUT_INT32 = 0, WVB_OUT_PCM = 1;
         internal const uint WVB_RF_CRC_ERROR = 1, WVB_RF_BLOCK_CHECKSUM = 32;
         internal const int WVB_E_CAPACITY = -4;

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define WVB_ABI_VERSION 2
+#define WVB_ABI_VERSION 3 /* 3: wvb_block_desc.checksum_off (was reserved), WVB_BF_BLOCK_CHECKSUM / WVB_RF_BLOCK_CHECKSUM, wvb_batch_decode_files, wvb_batch_dsd_to_dsf, wvb_block_checksum_ok */
 
 /* status codes */
 enum {

@@ -29,7 +29,7 @@ def test_struct_sizes_match_header(lib):
     from wavpackdecoder_b200 import _native as N
     assert C.sizeof(N.BlockDesc) == 160
     assert C.sizeof(N.BlockResult) == 16
-    assert lib.wvb_abi_version() == 2
+    assert lib.wvb_abi_version() == 3
     N.check_layout(lib)  # every field offset and size of the ctypes mirrors against the compiled C structs
 
 

@@ -171,7 +171,7 @@ def load():
     lib.wvb_host_alloc.restype = C.c_void_p
     lib.wvb_host_free.argtypes = [C.c_void_p]
     lib.wvb_host_free.restype = None
-    if lib.wvb_abi_version() != 2:
+    if lib.wvb_abi_version() != 3:
         raise RuntimeError("libwvb.so ABI version mismatch")
     check_layout(lib)
     _lib = lib
