@@ -866,6 +866,7 @@ int wvb_batch_decode_files(wvb_batch *b, const uint8_t *slab, size_t slab_bytes,
     // ---- index workers: files are handed out in order, each file's descriptors land in a block of its own ----
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
     threads = (int)std::min<size_t>((size_t)threads, std::max<size_t>(nfiles, 1));
+    if (threads > 2) --threads; // the calling thread works too (table layout, planning, launches): keep to the caller's core budget
     std::vector<std::vector<wvb_block_desc>> per_file(nfiles);
     std::unique_ptr<std::atomic<uint8_t>[]> done(new std::atomic<uint8_t>[nfiles ? nfiles : 1]);
     for (size_t i = 0; i < nfiles; i++) done[i].store(0, std::memory_order_relaxed);
