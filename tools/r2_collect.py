@@ -45,8 +45,8 @@ def main():
         _v, u = raw(path)
         rd = num("dram__bytes_read.sum") * unit[u["dram__bytes_read.sum"]]
         wr = num("dram__bytes_write.sum") * unit[u["dram__bytes_write.sum"]]
-        grid = int(num("launch__grid_size"))
-        blocks = 200000 if grid == (200000 + 127) // 128 else None
+        grid, cta = int(num("launch__grid_size")), int(num("launch__block_size"))
+        blocks = 200000 if (grid - 1) * cta < 200000 <= grid * cta else None  # one WavPack block per thread
         json.dump({"kernel": "k_decode_pcm<stereo,lossless,FixedDecorr<-2,3,2,18,18>,F16> (staged output)", "blocks_per_launch": blocks,
                    "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
                    "warp_instructions_per_launch": num("smsp__inst_executed.sum"),
