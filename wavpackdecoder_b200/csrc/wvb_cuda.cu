@@ -76,7 +76,7 @@ template <int CTA, bool STAGED = false, int RESERVE = 0> struct SharedColumn {
 // CTA: threads per CTA.  Nothing in the decoder is CTA-wide (no barrier, no shared data between threads), so the CTA size
 // only sets the granularity at which shared memory and registers are handed out and at which a launch's tail drains.
 // One-warp CTAs are the default: blocks with long term lists (150-250 words of decorrelation state per thread) fit 10 warps
-// per SM that way where 128-thread CTAs fit 8, and the 88-register kernels 23 warps instead of 20.
+// per SM that way where 128-thread CTAs fit 8; for the 88-register kernels (20 warps either way) the gain is the finer launch tail.
 constexpr int CTA_SMALL = 32, CTA_FIXED_D = 64;
 template <bool STEREO, bool HYB, bool GENFIX, class DEC, int MINB = 0, bool F16 = false, int CTA = CTA_THREADS>
 __global__ void __launch_bounds__(CTA, MINB)
