@@ -78,8 +78,9 @@ template <int CTA, bool STAGED = false, int RESERVE = 0> struct SharedColumn {
 // One-warp CTAs are the default: blocks with long term lists (150-250 words of decorrelation state per thread) fit 10 warps
 // per SM that way where 128-thread CTAs fit 8; for the 88-register kernels (20 warps either way) the gain is the finer launch tail.
 constexpr int CTA_SMALL = 32, CTA_FIXED_D = 64;
+// MINB: register cap, as the number of 128-thread CTAs' worth of threads that must fit an SM (0: no cap)
 template <bool STEREO, bool HYB, bool GENFIX, class DEC, int MINB = 0, bool F16 = false, int CTA = CTA_THREADS>
-__global__ void __launch_bounds__(CTA, MINB)
+__global__ void __launch_bounds__(CTA, MINB * 128 / CTA)
 k_decode_pcm(const uint8_t *__restrict__ in, const wvb_block_desc *__restrict__ descs, const uint32_t *__restrict__ order,
              uint32_t count, uint8_t *__restrict__ out, int out_format, wvb_block_result *__restrict__ results, uint32_t spread)
 {
@@ -203,8 +204,8 @@ pcm_kernel_t pcm_kernel(int variant)
     case wvb::V_STEREO | wvb::V_FIXED_C | wvb::V_F16: return k_decode_pcm<true, false, false, FixSC, 0, true>;
     // the 16-term list: 228-255 registers, i.e. 256 resident threads per SM whatever the CTA size; in 64-thread CTAs the
     // launch tail is finer (76.5 vs 79.0 ms per 60 000 blocks).  Capping the registers for a fifth CTA spills the history: 244 ms.
-    case wvb::V_STEREO | wvb::V_FIXED_D: return k_decode_pcm<true, false, false, FixSD, 4, false, CTA_FIXED_D>;
-    case wvb::V_STEREO | wvb::V_FIXED_D | wvb::V_F16: return k_decode_pcm<true, false, false, FixSD, 4, true, CTA_FIXED_D>;
+    case wvb::V_STEREO | wvb::V_FIXED_D: return k_decode_pcm<true, false, false, FixSD, 2, false, CTA_FIXED_D>;
+    case wvb::V_STEREO | wvb::V_FIXED_D | wvb::V_F16: return k_decode_pcm<true, false, false, FixSD, 2, true, CTA_FIXED_D>;
     case wvb::V_MONO | wvb::V_GENFIX: return k_decode_pcm<false, false, true, GenM>;
     case wvb::V_STEREO | wvb::V_GENFIX: return k_decode_pcm<true, false, true, GenS>;
     case wvb::V_MONO | wvb::V_GENFIX | wvb::V_HYBRID: return k_decode_pcm<false, true, true, GenM>;
