@@ -9,8 +9,8 @@ Workload (config.workload): BASELINE.json configs[1] -- 10 000 synthetic 16-bit 
 .wv files of 10 s per GPU (weak scaling: every rank decodes its own 10 000 files; shards share nothing).
 A step = one decode pass over the whole batch.
   value  : decoded complete samples/s, whole job, compressed input and PCM output resident in HBM
-  e2e    : same metric through the public C-ABI call with HOST (pinned) buffers: host index pass + H2D of the
-           compressed slab + kernels + D2H of the PCM, every step
+  e2e    : same metric through the public C-ABI call with HOST (pinned) buffers, every step: one wvb_batch_decode_files call =
+           host index pass (overlapped with the copies) + H2D of the compressed slab + kernels + D2H of the PCM
   e2e.pcie_ceiling: the same pinned buffers and byte counts moved with no decode (H2D and D2H at once, all ranks at once):
            the roofline of the end-to-end path; e2e.frac_of_ceiling = e2e / that
   roofline: algorithmic bytes (compressed block bytes in + PCM bytes out) / CUDA-event kernel time vs measured HBM peak
